@@ -1,0 +1,226 @@
+/* skeletor_b200.h — C ABI of libskeletor_b200.so
+ *
+ * Drop-in replacement for the compiled layer of nbia-astro/skeletor's particle
+ * hot path: the Cython module-level functions in skeletor/cython/*.pyx and
+ * ppic2's particle manager cppmove2 (picksc/ppic2/pplib2.c:607-981).  Each entry
+ * point cites the reference interface it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions (same as the reference):
+ *  - every buffer is allocated and owned by the caller (PyTorch tensors on the
+ *    Python side); the library never allocates, frees or keeps pointers between
+ *    calls.  All pointers are DEVICE pointers unless named h_*.
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *    the return value is a cudaError_t (0 = success) from launch-time checks.
+ *  - errors that the reference reports in-band (ihole[0] < 0) stay in-band.
+ *  - float64 only (reference types.pxd:6-8: real_t = double).  Arithmetic keeps
+ *    the reference's operation order and is compiled with -fmad=false, so
+ *    per-particle results are bit-identical to the reference's gcc -O2 x86-64
+ *    code; only deposition sums differ (summation order).
+ *
+ * Data layout in HBM:
+ *  - particles: structure of arrays, five contiguous double arrays x,y,vx,vy,vz
+ *    (reference: AoS particle_t, types.pxd:10-11).  x,y in grid units, y global.
+ *  - fields: C-order [myp][mx] of interleaved structs exactly as the reference's
+ *    Float3 (E,B: x,y,z) / Float4 (sources: t=rho,x,y,z) NumPy dtypes
+ *    (types.pyx:9-10, field.py:6-9); scalar fields [myp][mx] doubles.
+ *  - migration buffers: AoS rows of 5 doubles (x,y,vx,vy,vz), as sbufl/sbufr.
+ */
+#ifndef SKELETOR_B200_H
+#define SKELETOR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* grid_t of the reference (skeletor/cython/types.pxd:25-37, grid.py:7-67) */
+typedef struct {
+  int nx, ny;     /* global grid size */
+  int nyp, noff;  /* rows owned by this slab, first global row */
+  int lbx, lby;   /* guard layers = first active index */
+  int ubx, uby;   /* first upper guard index */
+  double dx, dy, Lx, Ly, x0, y0;
+  double edges[2]; /* [noff, noff+nyp] as doubles */
+} skb_grid_t;
+
+/* SoA particle arrays (device pointers) */
+typedef struct {
+  double *x, *y, *vx, *vy, *vz;
+} skb_particles_t;
+
+/* Tile ordering produced by skb_tile_sort().  A "cell key" is the tile-major
+ * index of the particle's E-gather/deposit stencil base cell in the extended
+ * [myp][mx] array; tiles are 2^tlx x 2^tly cells.  Particles [0, n_sorted) are
+ * ordered by key; [n_sorted, np) (e.g. arrivals not yet sorted) are unordered.
+ * Kernels never REQUIRE the ordering for correctness: a particle whose stencil
+ * is outside the shared-memory window of the tile it is filed under takes a
+ * global-memory path.  tile_offsets == NULL means "no ordering known". */
+typedef struct {
+  const int *tile_offsets;     /* [ntx*nty + 1] first particle of each tile */
+  const int *chunk_first_tile; /* [ceil(n_sorted/chunk)] tile of particle c*chunk */
+  int ntx, nty, tlx, tly;
+  int chunk;                   /* particles per CTA work item */
+  long long n_sorted;
+} skb_tiling_t;
+
+/* flags for the fused particle-boundary epilogue of skb_boris_push/skb_drift */
+#define SKB_EPI_NONE 0
+#define SKB_EPI_SHEAR 1      /* shear_periodic_y, particle_boundary.pyx:26-49 */
+#define SKB_EPI_PERIODIC_X 2 /* periodic_x,       particle_boundary.pyx:5-11  */
+#define SKB_EPI_HOLES 4      /* calculate_ihole (unordered list + count)      */
+
+typedef struct {
+  int flags;
+  double S, t;   /* shear rate and particle time AFTER the push (particles.py:154-155,175) */
+  int *ihole;    /* [ntmax+1]: ihole[0] = count (negated on overflow), then 1-based
+                    indices of particles with y < edges[0] or y >= edges[1] */
+  int ntmax;
+} skb_epilogue_t;
+
+int skb_version(void);
+const char *skb_error_string(int err);
+
+/* ---- push ----------------------------------------------------------------
+ * boris_push_cic/tsc(particles, E, B, qtmh, dt, grid)       particle_push.pyx:4,81
+ * modified_boris_push_cic/tsc(..., grid, Omega, S)          particle_push.pyx:40,117
+ * order: 1 = CIC, 2 = TSC.  modified != 0 adds the rotation/shear terms.
+ * tiling / epi may be NULL (plain reference semantics). */
+int skb_boris_push(skb_particles_t p, long long np, const double *E,
+                   const double *B, const skb_grid_t *grid, int order,
+                   double qtmh, double dt, int modified, double Omega, double S,
+                   const skb_tiling_t *tiling, const skb_epilogue_t *epi,
+                   void *stream);
+
+/* drift(particles, dt, grid)                                particle_push.pyx:159 */
+int skb_drift(skb_particles_t p, long long np, double dt, const skb_grid_t *grid,
+              const skb_epilogue_t *epi, void *stream);
+
+/* ---- particle boundaries ---------------------------------------------------
+ * periodic_x(particles, grid)                               particle_boundary.pyx:5  */
+int skb_periodic_x(skb_particles_t p, long long np, const skb_grid_t *grid,
+                   void *stream);
+/* shear_periodic_y(particles, grid, S, t)                   particle_boundary.pyx:26 */
+int skb_shear_periodic_y(skb_particles_t p, long long np, const skb_grid_t *grid,
+                         double S, double t, void *stream);
+/* calculate_ihole(particles, ihole, grid)                   particle_boundary.pyx:14
+ * Deterministic: the list is in ascending particle order, bit-identical to the
+ * reference's serial loop.  scratch: >= skb_ihole_scratch_ints(np) ints. */
+long long skb_ihole_scratch_ints(long long np);
+int skb_calculate_ihole(skb_particles_t p, long long np, int *ihole, int ntmax,
+                        const skb_grid_t *grid, int *scratch, void *stream);
+
+/* ---- particle manager: cppmove2(particles, npp, sbufl, sbufr, rbufl, rbufr,
+ *      ihole, info, grid)           ppic2_wrapper.pyx:51-67, pplib2.c:607-981
+ * split into its two local halves; the neighbour exchange between them
+ * (MPI_Isend/Irecv, pplib2.c:741-753) is done by the caller (NCCL send/recv, or
+ * a device copy when nvp == 1).
+ *
+ * skb_move_pack: for each listed hole, copy the particle into sbufl (y <
+ *   edges[0]; y += ny if rank == 0, pplib2.c:676-677) or sbufr (otherwise; y -=
+ *   ny if rank == nvp-1, :692-693).  counts[0] = #sbufl, counts[1] = #sbufr
+ *   (device ints, zeroed by the call).  A buffer overflow (> nbmax) is reported
+ *   as counts[2] = 1 and the surplus is NOT packed.
+ * skb_move_classify: multi-hop support (pplib2.c:756-866): split a received
+ *   buffer into particles that belong here (copied to `keep`, count in
+ *   counts[0]) and particles to pass further down / up (appended to sbufl /
+ *   sbufr with the edge-rank y wrap; counts[1], counts[2]; counts[3] = overflow).
+ *   The caller zeroes counts[0..3].
+ * skb_move_unpack: put `nin` incoming particles (AoS rows in `in`) into the
+ *   holes listed in ihole[1..nh], append what is left at np, or — if holes remain
+ *   — compact the tail into them (pplib2.c:883-952).  New count = np + nin - nh
+ *   (computed by the caller).  scratch: >= 2*nh + 8 ints. */
+int skb_move_pack(skb_particles_t p, const int *ihole, int nh, double *sbufl,
+                  double *sbufr, int nbmax, int *counts, const skb_grid_t *grid,
+                  int rank, int nvp, void *stream);
+int skb_move_classify(const double *rbuf, int nrecv, double *keep, double *sbufl,
+                      double *sbufr, int nbmax, int *counts, const skb_grid_t *grid,
+                      int rank, int nvp, void *stream);
+int skb_move_unpack(skb_particles_t p, long long np, const int *ihole, int nh,
+                    const double *in, int nin, int *scratch, void *stream);
+
+/* ---- deposit ---------------------------------------------------------------
+ * deposit_cic/tsc(particles, current, grid, S)               deposit.pyx:6,21
+ * Accumulates into `current` (Float4 [myp][mx]); the caller zeroes it when the
+ * reference's erase=True semantics are wanted (sources.py:37-38). */
+int skb_deposit(skb_particles_t p, long long np, double *current,
+                const skb_grid_t *grid, int order, double S,
+                const skb_tiling_t *tiling, void *stream);
+
+/* push_and_deposit_cic/tsc(particles, E, B, qtmh, dt, grid, ihole, current, S,
+ *                          update)                   push_and_deposit.pyx:10,91
+ * ihole semantics as skb_epilogue_t (unordered list); ihole[0] = -1 flags a
+ * particle that moved more than half a cell in the half step (:66-68). */
+int skb_push_and_deposit(skb_particles_t p, long long np, const double *E,
+                         const double *B, const skb_grid_t *grid, int order,
+                         double qtmh, double dt, int *ihole, int ntmax,
+                         double *current, double S, int update,
+                         const skb_tiling_t *tiling, void *stream);
+
+/* ---- tile sort (new component; reference's cppdsortp2yl is unused/broken) ----
+ * Counting sort of the SoA particle arrays by cell key, out of place.
+ * cell_counts: [ncells+1] ints with ncells = ntx*nty << (tlx+tly) (scratch);
+ * tile_offsets [ntx*nty+1] and
+ * chunk_first_tile [ceil(np/chunk)] are outputs; block_sums: >= 4100 ints.
+ * Ties (particles of one cell) end up in claim order, which is not contractual
+ * (neither is particle order in the reference, tests/test_skeletor.py:144-147);
+ * `stable` / `perm` are reserved for a stable variant and must be 0 / NULL. */
+int skb_tile_geometry(const skb_grid_t *grid, int tlx, int tly, int *ntx, int *nty);
+int skb_cell_keys(skb_particles_t p, long long np, const skb_grid_t *grid,
+                  int order, int tlx, int tly, int *keys, void *stream);
+int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long np,
+                  const skb_grid_t *grid, int order, int tlx, int tly, int chunk,
+                  int *cell_counts, int *block_sums, int *tile_offsets,
+                  int *chunk_first_tile, int stable, int *perm, void *stream);
+
+/* ---- guard cells (NumPy slicing in the reference) ----------------------------
+ * nc = doubles per cell (1, 3 or 4).
+ * skb_copy_guards: Field.copy_guards_y + copy_guards_x, field.py:73-98.
+ *   from_below / from_above: packed [lby][nx][nc] rows received from the
+ *   neighbours (the rank below's last active rows / the rank above's first active
+ *   rows); NULL = periodic wrap inside this slab (single rank).
+ * skb_add_guards: Sources.add_guards_x + add_guards_y + zeroing, sources.py:91-150.
+ *   phase 0: x fold over all rows (run before the shear remap / y exchange);
+ *   phase 1: y fold of `from_below` (the rank below's UPPER guard rows) and
+ *            `from_above` (the rank above's LOWER guard rows), or of this slab's
+ *            own guards when NULL, then zero every guard cell.
+ * skb_pack_rows: copy rows [iy0, iy0+nrows) x active columns into a packed buffer. */
+int skb_copy_guards(double *f, int nc, const skb_grid_t *grid,
+                    const double *from_below, const double *from_above,
+                    void *stream);
+int skb_add_guards(double *f, int nc, const skb_grid_t *grid, int phase,
+                   const double *from_below, const double *from_above,
+                   void *stream);
+int skb_pack_rows(const double *f, int nc, const skb_grid_t *grid, int iy0,
+                  int nrows, double *out, void *stream);
+/* refresh the x guards of one row after the spectral shear remap, field.py:169-171 */
+int skb_copy_guards_x_rows(double *f, int nc, const skb_grid_t *grid, int iy0,
+                           int nrows, void *stream);
+/* whole-array scale of every component: Sources.normalize, sources.py:61-63 */
+int skb_scale(double *f, long long n, double fac, void *stream);
+
+/* ---- finite differences: finite_difference.pyx:5-85 --------------------------
+ * f* point at the first element of a scalar plane with element stride `es`
+ * doubles (1 for a scalar field, 3/4 for a component of an interleaved field). */
+int skb_gradient(const double *f, int es, double *grad, const skb_grid_t *grid,
+                 void *stream);
+int skb_curl(const double *fx, const double *fy, const double *fz, int es,
+             double *curl, const skb_grid_t *grid, int down, void *stream);
+int skb_divergence(const double *fx, const double *fy, int es, double *div,
+                   const skb_grid_t *grid, void *stream);
+int skb_interp(const double *fx, const double *fy, const double *fz, int es,
+               double *out, const skb_grid_t *grid, int up, void *stream);
+
+/* Ohm.__call__ (ohm.py:35-75) fused into one pass over the active cells:
+ * E = -alpha grad(log rho) + eta curl_down(B) + ((curl_down(B) - J)/rho) x unstagger(B).
+ * Je_out / Bc_out (Float3, may be NULL) receive the reference's self.Je / self.B. */
+int skb_ohm(const double *sources, const double *B, double *E, double *Je_out,
+            double *Bc_out, const skb_grid_t *grid, double alpha, double eta,
+            void *stream);
+/* Faraday.__call__ (faraday.py:16-30): B -= dt * curl_up(E) on active cells */
+int skb_faraday(const double *E, double *B, double *dB_out,
+                const skb_grid_t *grid, double dt, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,353 @@
+// deposit.cu — CIC / TSC charge and current deposition, and the fused
+// push_and_deposit.
+//
+// Replaces deposit_cic/tsc (reference skeletor/cython/deposit.pyx:6-34,
+// deposit.pxd:3-118) and push_and_deposit_cic/tsc (push_and_deposit.pyx:10-170).
+//
+// Design (no per-particle atomics): particles are ordered by the cell of their
+// deposit stencil base (skb_tile_sort), so consecutive particles hit the same
+// 2x2 (CIC) / 3x3 (TSC) cells.  Each lane streams particles with coalesced loads
+// (lane-interleaved: lane l takes particles l, l+32, ... of its warp's range) and
+// accumulates the NS*NS*4 stencil sums of its CURRENT cell in registers.  When
+// any lane of the warp moves on to a new cell, the warp does one segmented
+// reduction over lanes (shuffles; segments = runs of lanes with equal cell) and
+// only the last lane of each run adds its totals to the CTA's shared-memory
+// window of the source grid.  At the end of a tile segment the window is added to
+// HBM once (coalesced rows, zero entries skipped).  Stencils that fall outside
+// the window (stale ordering, unsorted tail) go to HBM directly.  Per-particle
+// weights are formed exactly as the reference does (ty*tx, then *vx, ...), so the
+// only difference to the reference is the order of the summation.
+#include "common.cuh"
+#include "gather.cuh"
+#include <limits.h>
+
+#define ACC_EMPTY INT_MIN  // Acc.iy of a lane that holds no data
+
+#define DEP_THREADS 256
+
+struct DepParams {
+  double offx, offy;  // deposit.pyx:14-15
+  double S;
+};
+
+template <int NS>
+struct Acc {
+  double v[NS * NS * 4];
+  int ix, iy;  // stencil base cell (lower-left for CIC, centre for TSC); iy == ACC_EMPTY: no data
+};
+
+// Add the per-run totals to the shared window (or HBM).  Called by run tails only.
+template <int NS>
+__device__ __forceinline__ void emit(const Acc<NS> &a, double *sw, const Window &w,
+                                     int wstride, double *__restrict__ cur,
+                                     const DevGrid &g) {
+  const int lo = (NS == 3) ? 1 : 0;
+  const int x_lo = a.ix - lo, y_lo = a.iy - lo;
+  if (x_lo >= w.x0 && x_lo + NS <= w.x1 && y_lo >= w.y0 && y_lo + NS <= w.y1) {
+    double *b = sw + ((size_t)(y_lo - w.y0) * wstride + (x_lo - w.x0)) * 4;
+#pragma unroll
+    for (int r = 0; r < NS; r++)
+#pragma unroll
+      for (int c = 0; c < NS; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          atomicAdd(b + (r * wstride + c) * 4 + k, a.v[(r * NS + c) * 4 + k]);
+  } else if (x_lo >= 0 && x_lo + NS <= g.mx && y_lo >= 0 && y_lo + NS <= g.myp) {
+    double *b = cur + ((size_t)y_lo * g.mx + x_lo) * 4;
+#pragma unroll
+    for (int r = 0; r < NS; r++)
+#pragma unroll
+      for (int c = 0; c < NS; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          atomicAdd(b + ((size_t)r * g.mx + c) * 4 + k, a.v[(r * NS + c) * 4 + k]);
+  }
+  // else: outside the array (the reference would write out of bounds) — dropped
+}
+
+// Segmented reduction of every lane's accumulator over runs of equal cell, then
+// the run tails emit.  All 32 lanes must call this.
+template <int NS>
+__device__ __forceinline__ void warp_flush(Acc<NS> &a, double *sw, const Window &w,
+                                           int wstride, double *cur, const DevGrid &g) {
+  const int lane = threadIdx.x & 31;
+  const bool has = a.iy != ACC_EMPTY;
+  const int pix = __shfl_up_sync(SKB_FULL, a.ix, 1);
+  const int piy = __shfl_up_sync(SKB_FULL, a.iy, 1);
+  const bool head = (lane == 0) || (pix != a.ix) || (piy != a.iy);
+  const unsigned heads = __ballot_sync(SKB_FULL, head);
+  if (heads == 1u) {
+    // whole warp in one cell (the common case): plain butterfly-free reduction
+    if (has) {
+#pragma unroll
+      for (int i = 0; i < NS * NS * 4; i++) {
+        double s = a.v[i];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_down_sync(SKB_FULL, s, d);
+        a.v[i] = s;
+      }
+      if (lane == 0) emit<NS>(a, sw, w, wstride, cur, g);
+    }
+  } else {
+    // start lane of my run = highest head at or below my lane
+    const int seg0 = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+    for (int i = 0; i < NS * NS * 4; i++) {
+      double s = a.v[i];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double t = __shfl_up_sync(SKB_FULL, s, d);
+        if (lane - d >= seg0) s += t;
+      }
+      a.v[i] = s;
+    }
+    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+    if (tail && has) emit<NS>(a, sw, w, wstride, cur, g);
+  }
+#pragma unroll
+  for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+  a.iy = ACC_EMPTY;
+  a.ix = 0;
+}
+
+// Accumulate one particle (already positioned: xs = x + offx [+0.5 for TSC]).
+// deposit_particle_cic, deposit.pxd:3-44 / deposit_particle_tsc, deposit.pxd:46-118
+template <int ORDER>
+__device__ __forceinline__ void particle_terms(double xs, double ys, int &ix, int &iy,
+                                               double (&wx)[ORDER + 1],
+                                               double (&wy)[ORDER + 1]) {
+  if (ORDER == 1) {
+    double d, t;
+    cic_weights(xs, ix, d, t); wx[0] = t; wx[1] = d;
+    cic_weights(ys, iy, d, t); wy[0] = t; wy[1] = d;
+  } else {
+    tsc_weights(xs, ix, wx[0], wx[1], wx[2]);
+    tsc_weights(ys, iy, wy[0], wy[1], wy[2]);
+  }
+}
+
+template <int ORDER>
+__device__ __forceinline__ void accumulate(Acc<ORDER + 1> &a, const double (&wx)[ORDER + 1],
+                                           const double (&wy)[ORDER + 1], double vxr,
+                                           double vy, double vz) {
+  constexpr int NS = ORDER + 1;
+#pragma unroll
+  for (int r = 0; r < NS; r++)
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+      const double wgt = wy[r] * wx[c];
+      double *v = a.v + (r * NS + c) * 4;
+      v[0] += wgt;
+      v[1] += wgt * vxr;
+      v[2] += wgt * vy;
+      v[3] += wgt * vz;
+    }
+}
+
+__device__ __forceinline__ void zero_window(double *sw, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sw[i] = 0.0;
+}
+
+// add the shared window to the HBM source grid; zero entries (halo cells that no
+// particle touched) are skipped
+__device__ __forceinline__ void flush_window(const double *sw, const Window &w,
+                                             int wstride, double *__restrict__ cur,
+                                             const DevGrid &g) {
+  const int wx = (w.x1 - w.x0) * 4, wy = w.y1 - w.y0;
+  for (int idx = threadIdx.x; idx < wx * wy; idx += blockDim.x) {
+    int r = idx / wx, c = idx - r * wx;
+    double v = sw[(size_t)r * wstride * 4 + c];
+    if (v != 0.0) atomicAdd(cur + ((size_t)(w.y0 + r) * g.mx + w.x0) * 4 + c, v);
+  }
+}
+
+// MODE 0: deposit only (deposit.pyx:6-34)
+// MODE 1: push_and_deposit, update = False (predictor: particles untouched)
+// MODE 2: push_and_deposit, update = True            (push_and_deposit.pyx:10-170)
+struct FusedParams {
+  KickParams k;
+  double d2x, d2y;  // 0.5*dt/dx, 0.5*dt/dy, push_and_deposit.pyx:37-38
+  int *ihole;
+  int ntmax;
+};
+
+#define SKB_CFL_BIT 0x40000000
+
+template <int ORDER, int MODE>
+__global__ void __launch_bounds__(DEP_THREADS)
+deposit_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
+               const double *__restrict__ B, double *__restrict__ cur, DevGrid g,
+               DevTiling tl, DepParams q, FusedParams fq, int span, int wstride,
+               int wrows) {
+  constexpr int NS = ORDER + 1;
+  extern __shared__ double smem[];
+  double *sw = smem;                         // source window, 4 doubles per cell
+  const int wcells = wstride * wrows * 4;
+  double *sE = smem + wcells;                // MODE > 0: E and B windows
+  double *sB = sE + wstride * wrows * 3;
+
+  Acc<NS> a;
+#pragma unroll
+  for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+  a.iy = ACC_EMPTY; a.ix = 0;
+
+  SegmentIter it;
+  it.init(tl, np, span);
+  long long s0, s1;
+  int tile;
+  while (it.next(tl, s0, s1, tile)) {
+    Window w = tile_window(tile, tl, g);
+    if (tile >= 0) {
+      zero_window(sw, wcells);
+      if (MODE > 0) {
+        stage_window(sE, E, w, wstride, g);
+        stage_window(sB, B, w, wstride, g);
+      }
+      __syncthreads();
+    }
+    // Uniform trip count (every lane takes part in the warp collectives) and a
+    // warp-contiguous mapping: warp wv owns particles [wbeg, wend) and walks
+    // through them 32 at a time, i.e. through consecutive cells.
+    const long long n = s1 - s0;
+    const int nwarps = DEP_THREADS / 32;
+    const long long per_warp = ((n + nwarps - 1) / nwarps + 31) & ~31LL;
+    const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wbeg = s0 + (long long)wv * per_warp;
+    const long long wend = min(s1, wbeg + per_warp);
+    const long long witers = per_warp >> 5;
+    for (long long k = 0; k < witers; k++) {
+      const long long i = wbeg + k * 32 + lane;
+      const bool act = i < wend;
+      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+      if (act) { x = P.x[i]; y = P.y[i]; vx = P.vx[i]; vy = P.vy[i]; vz = P.vz[i]; }
+      if (MODE > 0 && act) {
+        const double xold = x, yold = y;
+        fields_and_kick<ORDER, false>(sE, sB, w, wstride, E, B, g, fq.k, x, y, vx, vy, vz);
+        x = x + vx * fq.d2x;   // first half of the drift
+        y = y + vy * fq.d2y;
+        // more than half a cell in half a step: push_and_deposit.pyx:66-68
+        if (fabs(x - xold) > 0.5 || fabs(y - yold) > 0.5) {
+          if (MODE == 2) atomicOr(fq.ihole, SKB_CFL_BIT);
+          else fq.ihole[0] = -1;
+        }
+      }
+      double xs = x + q.offx, ys = y + q.offy;
+      if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+      int ix, iy;
+      double wx[NS], wy[NS];
+      particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+      const bool changed = (a.iy != ACC_EMPTY) && (!act || iy != a.iy || ix != a.ix);
+      if (__any_sync(SKB_FULL, changed)) warp_flush<NS>(a, sw, w, wstride, cur, g);
+      if (act) {
+        // particle velocity relative to the background shear, deposit.pxd:24
+        const double vxr = vx + q.S * (y * g.dy + g.y0);
+        a.ix = ix; a.iy = iy;
+        accumulate<ORDER>(a, wx, wy, vxr, vy, vz);
+        if (MODE == 2) {
+          x = x + vx * fq.d2x;   // second half of the drift
+          y = y + vy * fq.d2y;
+          x = wrap_x(x, (double)g.nx);
+          if (y < g.e0 || y >= g.e1) {      // calculate_ihole_cdef
+            int slot = atomicAdd(fq.ihole, 1) & (SKB_CFL_BIT - 1);
+            if (slot < fq.ntmax) fq.ihole[slot + 1] = (int)i + 1;
+          }
+          P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
+        }
+      }
+    }
+    warp_flush<NS>(a, sw, w, wstride, cur, g);
+    if (tile >= 0) {
+      __syncthreads();
+      flush_window(sw, w, wstride, cur, g);
+      __syncthreads();
+    }
+  }
+}
+
+// decode ihole[0] = count | CFL bit into the reference's in-band convention
+__global__ void finalize_fused_ihole_kernel(int *ihole, int ntmax) {
+  int v = ihole[0];
+  int n = v & (SKB_CFL_BIT - 1);
+  if (v & SKB_CFL_BIT) ihole[0] = -1;
+  else if (n > ntmax) ihole[0] = -(n - 1);
+  else ihole[0] = n;
+}
+
+template <int ORDER, int MODE>
+static int launch_deposit(skb_particles_t p, long long np, const double *E,
+                          const double *B, double *current, const DevGrid &g,
+                          const DevTiling &tl, const DepParams &q,
+                          const FusedParams &fq, cudaStream_t st) {
+  // CTA work item: up to 8 chunks, fewer when that would leave SMs idle
+  int mult = 8;
+  while (mult > 1 && (np / ((long long)tl.chunk * mult)) < 4 * 148) mult >>= 1;
+  const int span = tl.chunk * mult;
+  const int ws = window_stride(tl), wr = window_rows(tl);
+  size_t smem = (size_t)ws * wr * (MODE > 0 ? 10 : 4) * sizeof(double);
+  long long nblk = (np + span - 1) / span;
+  auto k = deposit_kernel<ORDER, MODE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<(unsigned)nblk, DEP_THREADS, smem, st>>>(p, np, E, B, current, g, tl, q, fq, span, ws, wr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
+                           const skb_grid_t *grid, int order, double S,
+                           const skb_tiling_t *tiling, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (np <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  DevTiling tl = make_tiling(tiling);
+  DepParams q;
+  q.offx = g.lbx - 0.5;              // deposit.pyx:14-15
+  q.offy = g.lby - 0.5 - g.noff;
+  q.S = S;
+  FusedParams fq = {};
+  if (order == 1) return launch_deposit<1, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
+  if (order == 2) return launch_deposit<2, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
+  return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int skb_push_and_deposit(skb_particles_t p, long long np, const double *E,
+                                    const double *B, const skb_grid_t *grid, int order,
+                                    double qtmh, double dt, int *ihole, int ntmax,
+                                    double *current, double S, int update,
+                                    const skb_tiling_t *tiling, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGrid g = make_grid(grid);
+  DevTiling tl = make_tiling(tiling);
+  FusedParams fq;
+  fq.k = make_kick(g, qtmh, dt, 0.0, 0.0);
+  fq.d2x = 0.5 * dt / g.dx;
+  fq.d2y = 0.5 * dt / g.dy;
+  fq.ihole = ihole;
+  fq.ntmax = ntmax;
+  DepParams q;
+  q.offx = fq.k.offEx;               // offsetE reused, push_and_deposit.pyx:71
+  q.offy = fq.k.offEy;
+  q.S = S;
+  if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
+  if (update) {
+    cudaError_t e = cudaMemsetAsync(ihole, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (np > 0) {
+    int rc;
+    if (order == 1)
+      rc = update ? launch_deposit<1, 2>(p, np, E, B, current, g, tl, q, fq, st)
+                  : launch_deposit<1, 1>(p, np, E, B, current, g, tl, q, fq, st);
+    else
+      rc = update ? launch_deposit<2, 2>(p, np, E, B, current, g, tl, q, fq, st)
+                  : launch_deposit<2, 1>(p, np, E, B, current, g, tl, q, fq, st);
+    if (rc) return rc;
+  }
+  if (update) {
+    finalize_fused_ihole_kernel<<<1, 1, 0, st>>>(ihole, ntmax);
+    SKB_CHECK_LAUNCH();
+  }
+  return 0;
+}

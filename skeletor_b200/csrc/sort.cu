@@ -1,0 +1,254 @@
+// sort.cu — GPU counting sort of the SoA particle arrays by tile-major cell key.
+//
+// New component (the reference's cppdsortp2yl / particle_sort.py is unused and
+// broken); it exists to give push and deposit their locality:
+// after the sort every tile's particles are one contiguous range (tile_offsets)
+// and, inside a tile, particles of one stencil-base cell are consecutive.
+//
+// key(x, y) = tile-major index of (ixs, iys) = the E-gather / deposit stencil base
+// cell in the extended [myp][mx] array, computed with exactly the arithmetic the
+// deposit uses ((int)(x + (lbx - 0.5)) for CIC, (int)(x + (lbx - 0.5) + 0.5) for
+// TSC), clamped into the array.
+//
+// Passes: (1) histogram of keys (warp-aggregated integer atomics, 16 B/particle
+// read); (2) three-kernel exclusive scan over the cells -> cell starts, tile
+// offsets; (3) scatter: each warp claims slots per distinct key with one atomic
+// and moves the five arrays out of place (40 B read + 40 B written per particle);
+// (4) chunk -> first tile table for the CTA work items of push/deposit.
+// Order of particles inside one cell follows claim order (not contractual, like
+// the reference's particle order, tests/test_skeletor.py:144-147).
+#include "common.cuh"
+
+#define SORT_THREADS 256
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 16
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+struct KeyParams {
+  double offx, offy;
+  int order, tlx, tly, ntx, mx, myp;
+};
+
+static KeyParams make_keyparams(const DevGrid &g, int order, int tlx, int tly) {
+  KeyParams k;
+  k.offx = g.lbx - 0.5;
+  k.offy = g.lby - 0.5 - g.noff;
+  k.order = order; k.tlx = tlx; k.tly = tly;
+  k.mx = g.mx; k.myp = g.myp;
+  k.ntx = (g.mx + (1 << tlx) - 1) >> tlx;
+  return k;
+}
+
+__device__ __forceinline__ int cell_key(double x, double y, const KeyParams &k) {
+  double xs = x + k.offx, ys = y + k.offy;
+  if (k.order == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+  int ix = (int)xs, iy = (int)ys;
+  ix = min(max(ix, 0), k.mx - 1);
+  iy = min(max(iy, 0), k.myp - 1);
+  const int mxm = (1 << k.tlx) - 1, mym = (1 << k.tly) - 1;
+  return ((((iy >> k.tly) * k.ntx + (ix >> k.tlx)) << (k.tlx + k.tly)) |
+          ((iy & mym) << k.tlx) | (ix & mxm));
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+keys_kernel(skb_particles_t P, long long np, KeyParams kp, int *keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) keys[i] = cell_key(P.x[i], P.y[i], kp);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+count_kernel(skb_particles_t P, long long np, KeyParams kp, int *counts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < np;
+  int key = act ? cell_key(P.x[i], P.y[i], kp) : -1;
+  // one atomic per distinct key in the warp
+  unsigned peers = __match_any_sync(SKB_FULL, key);
+  const int lane = threadIdx.x & 31;
+  if (act && lane == __ffs(peers) - 1) atomicAdd(counts + key, __popc(peers));
+}
+
+// ---- exclusive scan over n ints, in place, 3 kernels -------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const int *__restrict__ a, int n, int *block_sums) {
+  __shared__ int red[SCAN_THREADS / 32];
+  long long base = (long long)blockIdx.x * SCAN_TILE;
+  int s = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    long long i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += a[i];
+  }
+  for (int d = 16; d >= 1; d >>= 1) s += __shfl_down_sync(SKB_FULL, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; w++) t += red[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_top_kernel(int *block_sums, int nb) {
+  // single CTA, exclusive scan of nb <= a few thousand entries
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = (i < nb) ? block_sums[i] : 0;
+    int s = v;
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(SKB_FULL, s, d);
+      if (lane >= d) s += t;
+    }
+    if (lane == 31) warp_tot[wv] = s;
+    __syncthreads();
+    if (wv == 0) {
+      int t = warp_tot[lane];
+      int u = t;
+      for (int d = 1; d < 32; d <<= 1) {
+        int r = __shfl_up_sync(SKB_FULL, u, d);
+        if (lane >= d) u += r;
+      }
+      warp_tot[lane] = u - t;  // exclusive warp offsets
+      if (lane == 31) warp_tot[31] = u - t;
+    }
+    __syncthreads();
+    int carry = carry_s;
+    int excl = carry + warp_tot[wv] + s - v;
+    if (i < nb) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+// in-place: a[i] <- exclusive prefix; also records tile starts
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(int *a, int n, const int *__restrict__ block_sums, int cells_log2,
+                  int *tile_offsets) {
+  __shared__ int warp_tot[SCAN_THREADS / 32];
+  __shared__ int carry_s;
+  long long base = (long long)blockIdx.x * SCAN_TILE;
+  if (threadIdx.x == 0) carry_s = block_sums[blockIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    long long i = base + k * SCAN_THREADS + threadIdx.x;
+    int v = (i < n) ? a[i] : 0;
+    int s = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(SKB_FULL, s, d);
+      if (lane >= d) s += t;
+    }
+    if (lane == 31) warp_tot[wv] = s;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wv; w++) woff += warp_tot[w];
+    int excl = carry_s + woff + s - v;
+    if (i < n) {
+      a[i] = excl;
+      if ((i & ((1LL << cells_log2) - 1)) == 0) tile_offsets[i >> cells_log2] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+// scatter: cell_pos[key] holds the next free slot of the cell (starts at the
+// exclusive prefix); a warp claims a block of slots per distinct key.
+__global__ void __launch_bounds__(SORT_THREADS)
+scatter_kernel(skb_particles_t in, skb_particles_t out, long long np, KeyParams kp,
+               int *cell_pos) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < np;
+  double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+  if (act) { x = in.x[i]; y = in.y[i]; vx = in.vx[i]; vy = in.vy[i]; vz = in.vz[i]; }
+  int key = act ? cell_key(x, y, kp) : -1;
+  unsigned peers = __match_any_sync(SKB_FULL, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (act && lane == leader) base = atomicAdd(cell_pos + key, __popc(peers));
+  base = __shfl_sync(SKB_FULL, base, leader);
+  if (act) {
+    long long d = (long long)base + __popc(peers & ((1u << lane) - 1u));
+    out.x[d] = x; out.y[d] = y; out.vx[d] = vx; out.vy[d] = vy; out.vz[d] = vz;
+  }
+}
+
+// after the scatter cell_pos[k] = start of cell k+1; shift back so that on return
+// the array holds the exclusive prefix again (cell starts), entry [ncells] = np
+__global__ void __launch_bounds__(256)
+chunk_table_kernel(const int *__restrict__ tile_offsets, int ntiles, int chunk,
+                   int *chunk_first_tile) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  long long a = tile_offsets[t], b = tile_offsets[t + 1];
+  if (b <= a) return;
+  // chunks whose first particle c*chunk lies in [a, b)
+  for (long long c = (a + chunk - 1) / chunk; c * chunk < b; c++) chunk_first_tile[c] = t;
+}
+
+extern "C" int skb_tile_geometry(const skb_grid_t *grid, int tlx, int tly, int *ntx,
+                                 int *nty) {
+  int mx = grid->nx + 2 * grid->lbx, myp = grid->nyp + 2 * grid->lby;
+  *ntx = (mx + (1 << tlx) - 1) >> tlx;
+  *nty = (myp + (1 << tly) - 1) >> tly;
+  return 0;
+}
+
+extern "C" int skb_cell_keys(skb_particles_t p, long long np, const skb_grid_t *grid,
+                             int order, int tlx, int tly, int *keys, void *stream) {
+  if (np <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  keys_kernel<<<(unsigned)((np + SORT_THREADS - 1) / SORT_THREADS), SORT_THREADS, 0,
+                (cudaStream_t)stream>>>(p, np, kp, keys);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long np,
+                             const skb_grid_t *grid, int order, int tlx, int tly,
+                             int chunk, int *cell_counts, int *block_sums,
+                             int *tile_offsets, int *chunk_first_tile, int stable,
+                             int *perm, void *stream) {
+  (void)perm;
+  if (stable) return (int)cudaErrorNotSupported;  // reserved
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  const int ntiles = ntx * nty;
+  const long long ncells = (long long)ntiles << (tlx + tly);
+  const int n = (int)ncells + 1;  // one extra entry: total
+  const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb > 4096) return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(cell_counts, 0, sizeof(int) * (size_t)n, st);
+  if (e != cudaSuccess) return (int)e;
+  const unsigned pblk = (unsigned)((np + SORT_THREADS - 1) / SORT_THREADS);
+  if (np > 0) {
+    count_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, np, kp, cell_counts);
+    SKB_CHECK_LAUNCH();
+  }
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums);
+  SKB_CHECK_LAUNCH();
+  scan_top_kernel<<<1, 1024, 0, st>>>(block_sums, nb);
+  SKB_CHECK_LAUNCH();
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums, tlx + tly,
+                                                tile_offsets);
+  SKB_CHECK_LAUNCH();
+  if (np > 0) {
+    chunk_table_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(tile_offsets, ntiles, chunk,
+                                                             chunk_first_tile);
+    SKB_CHECK_LAUNCH();
+    scatter_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
+    SKB_CHECK_LAUNCH();
+  }
+  return 0;
+}

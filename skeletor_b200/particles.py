@@ -1,0 +1,380 @@
+"""Particles: the ions of one y-slab, structure-of-arrays in device memory.
+
+Mirrors skeletor.Particles (reference skeletor/particles.py:5-265): same
+constructor, attributes (N, time, charge, mass, n0, order, ihole, sbufl/r, rbufl/r,
+info, sources) and methods (initialize, push, push_modified, push_and_deposit,
+drift, periodic_x, periodic_y, shear_periodic_y, move, deposit).  The reference is
+a NumPy structured array of AoS records; here the five coordinates are five
+contiguous device arrays (one [5][Nmax] tensor, plus a second one the tile sort
+ping-pongs with), and `ions['x']`, `ions[:N]` return device-backed proxies.
+
+Every method that changes positions ends with the tile sort (skb_tile_sort), so
+push gathers from shared-memory field tiles and deposit accumulates runs of
+same-cell particles in registers.  The ordering is a performance property only:
+kernels are correct for any order (user code may overwrite coordinates at will).
+"""
+import ctypes as C
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from .array import DeviceArray
+from .field import _stream
+from .sources import Sources
+from .types import Particle
+
+# tile = 2^TLX x 2^TLY stencil-base cells; chunk = particles per work-item unit
+TLX, TLY, CHUNK = 4, 4, 2048
+
+_ROW = {"x": 0, "y": 1, "vx": 2, "vy": 3, "vz": 4}
+
+
+class ParticleSlice:
+    """ions[a:b] — converts to a structured NumPy array; fields are device proxies"""
+
+    def __init__(self, parent, sl):
+        self.parent, self.sl = parent, sl
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.parent._data[:, self.sl].t().contiguous().cpu().numpy()
+        out = np.zeros(a.shape[0], Particle)
+        for k, r in _ROW.items():
+            out[k] = a[:, r]
+        return out
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.parent[key][self.sl]
+        return np.asarray(self)[key]
+
+    def __setitem__(self, key, val):
+        self.parent[key][self.sl] = val
+
+    def __len__(self):
+        return len(range(*self.sl.indices(self.parent.size)))
+
+    @property
+    def shape(self):
+        return (len(self),)
+
+    @property
+    def size(self):
+        return len(self)
+
+
+class Particles:
+    """Container class for particles in a given subdomain"""
+
+    def __init__(self, manifold, Nmax,
+                 time=0.0, charge=1.0, mass=1.0, n0=1.0, order=1):
+        _lib.require_cuda()
+        msg = 'Interpolation order {} needs more guard layers'.format(order)
+        # The number of guard layers on each side needs to be equal to
+        # int(ceil(order*0.5 + 0.5)) (particles.py:15-19)
+        assert manifold.lbx >= order//2 + 1, msg
+
+        Nmax = int(Nmax)
+        # Size of buffer for passing particles between processors
+        nbmax = int(max(0.1*Nmax, 1))
+        # Size of ihole buffer for particles leaving processor
+        ntmax = 2*nbmax
+        self.nbmax, self.ntmax = nbmax, ntmax
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        # phase space coordinates, SoA: rows x, y, vx, vy, vz
+        self._data = torch.zeros((5, Nmax), **f64)
+        self._alt = torch.zeros((5, Nmax), **f64)      # sort ping-pong buffer
+        self.size = Nmax
+
+        self.charge = charge
+        self.mass = mass
+        self.n0 = n0
+        self.order = order
+        self.manifold = manifold
+
+        # Location of hole left in particle arrays (particles.py:40)
+        self.ihole = torch.zeros(ntmax, **i32)
+        # Buffer arrays for the neighbour exchange (AoS rows of 5 doubles)
+        self.sbufl = torch.zeros((nbmax, 5), **f64)
+        self.sbufr = torch.zeros((nbmax, 5), **f64)
+        self.rbufl = torch.zeros((nbmax, 5), **f64)
+        self.rbufr = torch.zeros((nbmax, 5), **f64)
+        self._keep = torch.zeros((2*nbmax, 5), **f64)
+        self._counts = torch.zeros(8, **i32)
+        self._move_scratch = torch.zeros(2*ntmax + 8, **i32)
+        self._ihole_scratch = torch.zeros(
+            int(_lib.load().skb_ihole_scratch_ints(Nmax)) + 1, **i32)
+
+        # Create source array
+        self.sources = Sources(manifold)
+        # Info array used for checking errors in particle move
+        self.info = np.zeros(7, np.int32)
+        # Set initial time
+        self.time = time
+        self.N = 0
+
+        # tile-sort state
+        ntx, nty = C.c_int(), C.c_int()
+        _lib.load().skb_tile_geometry(manifold.c, TLX, TLY, C.byref(ntx), C.byref(nty))
+        self._ntx, self._nty = ntx.value, nty.value
+        ntiles = self._ntx*self._nty
+        self._cell_counts = torch.zeros((ntiles << (TLX + TLY)) + 1, **i32)
+        self._block_sums = torch.zeros(4100, **i32)
+        self._tile_offsets = torch.zeros(ntiles + 1, **i32)
+        self._chunk_first = torch.zeros(Nmax//CHUNK + 2, **i32)
+        self._n_sorted = 0
+        self._sorted = False
+        self.sort_enabled = True
+
+    # -- NumPy-like surface -------------------------------------------------------
+    @property
+    def shape(self):
+        return (self.size,)
+
+    @property
+    def dtype(self):
+        return Particle
+
+    def __len__(self):
+        return self.size
+
+    def _touched(self):
+        self._sorted = False
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return DeviceArray(self._data[_ROW[key]], on_write=self._touched)
+        if isinstance(key, slice):
+            return ParticleSlice(self, key)
+        return np.asarray(ParticleSlice(self, slice(None)))[key]
+
+    def __setitem__(self, key, val):
+        if isinstance(key, str):
+            self[key][...] = val
+        elif isinstance(key, slice):
+            a = np.asarray(val)
+            for k in _ROW:
+                self[k][key] = a[k]
+        else:
+            raise TypeError("unsupported particle assignment")
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(ParticleSlice(self, slice(None)))
+
+    # -- C ABI views ---------------------------------------------------------------
+    @staticmethod
+    def _soa(t):
+        n = t.shape[1]*8
+        p = t.data_ptr()
+        return _lib.ParticlesT(p, p + n, p + 2*n, p + 3*n, p + 4*n)
+
+    @property
+    def _c(self):
+        return self._soa(self._data)
+
+    def _tiling_c(self):
+        if not (self._sorted and self._n_sorted > 0):
+            return None
+        return C.pointer(_lib.TilingT(
+            self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(),
+            self._ntx, self._nty, TLX, TLY, CHUNK, self._n_sorted))
+
+    def _epilogue(self, flags, S=0.0):
+        return C.pointer(_lib.EpilogueT(flags, float(S), float(self.time),
+                                        self.ihole.data_ptr(), self.ntmax - 1))
+
+    # -- tile sort -------------------------------------------------------------------
+    def sort(self):
+        """Counting sort by tile-major stencil-base cell (skb_tile_sort)."""
+        if self.N == 0 or not self.sort_enabled:
+            self._sorted = False
+            return
+        _lib.call("skb_tile_sort", self._c, self._soa(self._alt), self.N,
+                  self.manifold.c, self.order, TLX, TLY, CHUNK,
+                  self._cell_counts.data_ptr(), self._block_sums.data_ptr(),
+                  self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(), 0,
+                  None, _stream())
+        self._data, self._alt = self._alt, self._data
+        self._n_sorted = self.N
+        self._sorted = True
+
+    def _ensure_sorted(self):
+        if not self._sorted:
+            self.sort()
+
+    # -- reference API ---------------------------------------------------------------
+    def initialize(self, x, y, vx, vy, vz):
+        """particles.py:77-102 (positions in physical units, host arrays)"""
+        m = self.manifold
+        x, y, vx, vy, vz = (np.asarray(a, dtype=np.float64) for a in (x, y, vx, vy, vz))
+        ind = np.logical_and(y >= m.y0 + m.edges[0]*m.dy,
+                             y < m.y0 + m.edges[1]*m.dy)
+        self.N = int(np.sum(ind))
+        assert self.size >= self.N
+        if self.size < int(5/4*self.N):
+            msg = "Particle array is probably not large enough"
+            warn(msg + " (N={}, Nmax={})".format(self.N, self.size))
+        host = np.stack([(x[ind] - m.x0)/m.dx, (y[ind] - m.y0)/m.dy,
+                         vx[ind], vy[ind], vz[ind]])
+        self._data[:, :self.N] = torch.as_tensor(host, device=self.device)
+        self._sorted = False
+
+    def deposit(self, **kwds):
+        self.sources.deposit(self, **kwds)
+
+    def _ihole_count(self):
+        n = int(self.ihole[0].item())
+        # Check for ihole overflow error (particles.py:113-117)
+        if n < 0:
+            msg = "ihole overflow error: ntmax={}, ierr={}"
+            raise RuntimeError(msg.format(self.ihole.numel() - 1, -n))
+        return n
+
+    def move(self):
+        """Move particles that left the slab to the neighbouring ranks: ppic2's
+        cppmove2 (pplib2.c:607-981) as pack -> NCCL ring exchange -> unpack."""
+        g = self.manifold
+        comm = g.comm
+        gc = g.c
+        st = _stream()
+        nh = self._ihole_count()
+        cnt = self._counts
+        _lib.call("skb_move_pack", self._c, self.ihole.data_ptr(), nh,
+                  self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
+                  cnt.data_ptr(), gc, comm.rank, comm.size, st)
+        nl, nr, ovf = cnt[:3].tolist()
+        if ovf:
+            raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
+        nkeep = 0
+        for it in range(2000):
+            if comm.size == 1:
+                # nvp == 1: rbufl = sbufr, rbufr = sbufl (pplib2.c:715-730)
+                from_below, from_above = self.sbufr[:nr], self.sbufl[:nl]
+                nb_, na_ = nr, nl
+            else:
+                nb_, na_ = comm.exchange_counts(nr, nl)
+                from_below, from_above = comm.ring_exchange(
+                    self.sbufr[:nr], self.sbufl[:nl],
+                    self.rbufl[:nb_], self.rbufr[:na_])
+            # keep what belongs here, pass the rest on (pplib2.c:756-866)
+            cnt.zero_()
+            cnt[0] = nkeep
+            if comm.size == 1:
+                # sbufl/sbufr are both source and destination: classify from copies
+                from_below, from_above = from_below.clone(), from_above.clone()
+            for buf, n in ((from_below, nb_), (from_above, na_)):
+                _lib.call("skb_move_classify", buf.data_ptr(), n,
+                          self._keep.data_ptr(), self.sbufl.data_ptr(),
+                          self.sbufr.data_ptr(), self.nbmax, cnt.data_ptr(), gc,
+                          comm.rank, comm.size, st)
+            nkeep, nl, nr, ovf = cnt[:4].tolist()
+            if ovf or nkeep > self._keep.shape[0]:
+                raise RuntimeError("particle buffer overflow while forwarding")
+            more = nl + nr
+            if comm.size > 1:
+                from .comm import MAX
+                more = comm.allreduce(more, op=MAX)
+            if more == 0:
+                break
+        new_n = self.N + nkeep - nh
+        if new_n > self.size:
+            self.info[0] = new_n - self.size
+            raise RuntimeError("particle overflow error, ierr = {}".format(
+                new_n - self.size))
+        _lib.call("skb_move_unpack", self._c, self.N, self.ihole.data_ptr(), nh,
+                  self._keep.data_ptr(), nkeep, self._move_scratch.data_ptr(), st)
+        self.N = new_n
+        self.info[1] = self.info[2] = new_n
+        self._sorted = False
+
+    def periodic_x(self):
+        """Applies periodic boundaries on particles along x"""
+        _lib.call("skb_periodic_x", self._c, self.N, self.manifold.c, _stream())
+
+    def calculate_ihole(self):
+        _lib.call("skb_calculate_ihole", self._c, self.N, self.ihole.data_ptr(),
+                  self.ntmax - 1, self.manifold.c, self._ihole_scratch.data_ptr(),
+                  _stream())
+
+    def periodic_y(self):
+        """Applies periodic boundaries on particles along y: calculates ihole and
+        then moves particles between processors (particles.py:133-143)."""
+        self.calculate_ihole()
+        self.move()
+
+    def shear_periodic_y(self):
+        """Shearing periodic boundaries along y (particles.py:145-157)."""
+        _lib.call("skb_shear_periodic_y", self._c, self.N, self.manifold.c,
+                  float(self.manifold.S), float(self.time), _stream())
+        self.periodic_y()
+
+    def _push(self, E, B, dt, modified):
+        if self.order not in (1, 2):
+            msg = 'Interpolation order {} not implemented.'
+            raise RuntimeError(msg.format(self.order))
+        m = self.manifold
+        # Update time
+        self.time += dt
+        qtmh = self.charge/self.mass*dt/2
+        shear = hasattr(m, 'S')
+        # kernel + fused boundary epilogue: shear boost, hole list, x wrap
+        # (particles.py:179-188 in one pass over the particles)
+        flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X | (_lib.EPI_SHEAR if shear else 0)
+        self._ensure_sorted()
+        _lib.call("skb_boris_push", self._c, self.N, E.ptr, B.ptr, m.c, self.order,
+                  float(qtmh), float(dt), int(modified),
+                  float(getattr(m, 'Omega', 0.0)) if modified else 0.0,
+                  float(getattr(m, 'S', 0.0)) if modified else 0.0,
+                  self._tiling_c(), self._epilogue(flags, getattr(m, 'S', 0.0)),
+                  _stream())
+        self.move()
+        self.sort()
+
+    def push(self, E, B, dt):
+        """A standard Boris push which updates positions and velocities
+        (particles.py:159-188).  If shear is turned on, E needs to be E_star and B
+        needs to be B_star."""
+        self._push(E, B, dt, False)
+
+    def push_modified(self, E, B, dt):
+        """particles.py:233-257"""
+        self._push(E, B, dt, True)
+
+    def push_and_deposit(self, E, B, dt, update=True):
+        """Updates positions and velocities and deposits charge and currents at the
+        half step; update=False only computes the new sources (predictor step).
+        particles.py:190-231.  Does not work with shear (S = 0, as the reference)."""
+        if self.order not in (1, 2):
+            msg = 'Interpolation order {} not implemented.'
+            raise RuntimeError(msg.format(self.order))
+        self.time += dt
+        qtmh = self.charge/self.mass*dt/2
+        S = 0.0
+        src = self.sources
+        src.t.zero_()
+        self._ensure_sorted()
+        _lib.call("skb_push_and_deposit", self._c, self.N, E.ptr, B.ptr,
+                  self.manifold.c, self.order, float(qtmh), float(dt),
+                  self.ihole.data_ptr(), self.ntmax - 1, src.ptr, S, int(bool(update)),
+                  self._tiling_c(), _stream())
+        src.boundaries_set = False
+        src.normalize(self)
+        src.set_boundaries()
+        if update:
+            self.move()
+            self.sort()
+        elif int(self.ihole[0].item()) < 0:
+            self._ihole_count()
+
+    def drift(self, dt):
+        """particles.py:259-265: drift, then periodic_x and periodic_y"""
+        flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X
+        _lib.call("skb_drift", self._c, self.N, float(dt), self.manifold.c,
+                  self._epilogue(flags), _stream())
+        self.move()
+        self.sort()

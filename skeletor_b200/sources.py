@@ -1,0 +1,83 @@
+"""Sources: charge and current density (rho, Jx, Jy, Jz) deposited from particles.
+
+Mirrors skeletor.Sources (reference skeletor/sources.py:5-192)."""
+import torch
+
+from . import _lib
+from .field import Field, _stream
+from .types import Float4
+
+
+class Sources(Field):
+
+    def __init__(self, manifold, **kwds):
+        kwds.pop("dtype", None)
+        super().__init__(manifold, dtype=Float4, **kwds)
+
+    @property
+    def rho(self):
+        return self['t']
+
+    @property
+    def Jx(self):
+        return self['x']
+
+    @property
+    def Jy(self):
+        return self['y']
+
+    @property
+    def Jz(self):
+        return self['z']
+
+    def deposit(self, particles, erase=True, set_boundaries=False):
+        """sources.py:27-50"""
+        if particles.order not in (1, 2):
+            msg = 'Interpolation order {} not implemented.'
+            raise RuntimeError(msg.format(particles.order))
+        if erase:
+            self.t.zero_()
+        # Rate of shear
+        S = getattr(self.grid, 'S', 0.0)
+        particles._ensure_sorted()
+        _lib.call("skb_deposit", particles._c, particles.N, self.ptr, self.grid.c,
+                  particles.order, float(S), particles._tiling_c(), _stream())
+        self.boundaries_set = False
+        self.normalize(particles)
+        if set_boundaries:
+            self.set_boundaries()
+
+    def normalize(self, particles):
+        """Normalize the charge and current densities such that the mean charge
+        density is equal to particle.n0 (sources.py:52-63; guards included)."""
+        from .comm import SUM
+        N = self.grid.comm.allreduce(int(particles.N), op=SUM)
+        fac = particles.charge*particles.n0*self.grid.nx*self.grid.ny/N
+        _lib.call("skb_scale", self.ptr, self.t.numel(), float(fac), _stream())
+
+    def set_boundaries(self):
+        self.add_guards()
+        self.copy_guards()
+
+    def add_guards(self):
+        "Add data from guard cells to corresponding active cells (sources.py:117-150)."
+        g = self.grid
+        gc = g.c
+        # x-boundaries, all rows
+        _lib.call("skb_add_guards", self.ptr, self.nc, gc, 0, None, None, _stream())
+        if self.shear:
+            # Translate the y-ghostzones (sources.py:128-139)
+            if g.comm.rank == g.comm.size - 1:
+                self._translate_boundary(g.Ly*g.S*self.time, g.uby, g.lby)
+            if g.comm.rank == 0:
+                self._translate_boundary(-g.Ly*g.S*self.time, 0, g.lby)
+        # y-boundaries (+ zeroing of all guards)
+        if g.comm.size == 1:
+            _lib.call("skb_add_guards", self.ptr, self.nc, gc, 1, None, None, _stream())
+        else:
+            # my upper guards go up, my lower guards go down (sources.py:110-111)
+            up = self._pack_rows(g.uby, g.lby)
+            dn = self._pack_rows(0, g.lby)
+            from_below, from_above = self._halo_exchange(up, dn)
+            _lib.call("skb_add_guards", self.ptr, self.nc, gc, 1,
+                      from_below.data_ptr(), from_above.data_ptr(), _stream())

@@ -1,0 +1,460 @@
+"""-m gpu parity tests: every C-ABI kernel of libskeletor_b200 against the CPU
+oracle (oracle/oracle.py, itself pinned to the unmodified reference) on the same
+seeded inputs.  Bar: bit-exact for per-particle work, integer work and copies;
+<= 1e-12 relative for deposited sums (summation order) and the log in Ohm."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from refutil import bits, random_field, random_particles
+import gpuutil as gu
+from skeletor_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [
+    dict(nx=32, ny=32, lbx=1, lby=1),
+    dict(nx=16, ny=64, lbx=2, lby=2, Lx=2.0, Ly=1.0, x0=-0.5, y0=-0.25),
+    dict(nx=64, ny=32, rank=1, size=4, lbx=2, lby=3, Lx=1.0, Ly=3.0),
+    dict(nx=128, ny=96, rank=2, size=3, lbx=2, lby=2),
+]
+
+
+def rel(a, b):
+    a = np.ascontiguousarray(a).view(np.float64).ravel()
+    b = np.ascontiguousarray(b).view(np.float64).ravel()
+    return np.abs(a - b).max()/max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("gk", GRIDS)
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("modified", [False, True])
+@pytest.mark.parametrize("sort", [False, True])
+def test_push_bitexact(gk, order, modified, sort):
+    if order == 2 and gk["lbx"] < 2:
+        pytest.skip("TSC needs two guard layers")
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(1)
+    n = 20000
+    p = random_particles(g, n, rng)
+    E = random_field(g, orc.Float3, rng)
+    B = random_field(g, orc.Float3, rng)
+    qtmh, dt, Omega, S = 0.37*0.05/2, 0.05, 1.0, -1.5
+    exp = p.copy()
+    orc.push(exp, E, B, g, order, qtmh, dt, modified, Omega, S)
+    t = gu.soa(p)
+    til = None
+    if sort:
+        tl = gu.Tiling(g, order)
+        t = tl.sort(t, n)
+        til = tl.c()
+    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
+              gu.dev(B).data_ptr(), gu.cgrid(g), order, qtmh, dt, int(modified), Omega,
+              S, til, None, gu.stream())
+    got = gu.aos(t)
+    if sort:
+        assert np.array_equal(gu.sorted_rows(got), gu.sorted_rows(exp))
+    else:
+        assert np.array_equal(bits(got), bits(exp))
+
+
+@pytest.mark.parametrize("gk", GRIDS[:3])
+@pytest.mark.parametrize("shear", [False, True])
+def test_push_epilogue_matches_reference_sequence(gk, shear):
+    """fused epilogue == push; shear_periodic_y; calculate_ihole; periodic_x"""
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(2)
+    n = 30000
+    p = random_particles(g, n, rng, vth=8.0)
+    E = random_field(g, orc.Float3, rng, -0.01, 0.01)
+    B = g.field(orc.Float3)
+    qtmh, dt, S, time = 0.01, 0.05*g.dx, -1.5, 0.83
+    exp = p.copy()
+    orc.push(exp, E, B, g, 1, qtmh, dt)
+    if shear:
+        orc.shear_periodic_y(exp, g, S, time)
+    ih_exp = np.zeros(n + 1, np.int32)
+    orc.calculate_ihole(exp, ih_exp, g)
+    orc.periodic_x(exp, g)
+    t = gu.soa(p)
+    ihole = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X | (_lib.EPI_SHEAR if shear else 0)
+    epi = C.pointer(_lib.EpilogueT(flags, S, time, ihole.data_ptr(), n))
+    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
+              gu.dev(B).data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
+              gu.stream())
+    assert np.array_equal(bits(gu.aos(t)), bits(exp))
+    ih = ihole.cpu().numpy()
+    assert ih[0] == ih_exp[0] > 0
+    assert np.array_equal(np.sort(ih[1:ih[0] + 1]), ih_exp[1:ih_exp[0] + 1])
+    # overflowing hole list: in-band negative count, as the reference
+    small = torch.zeros(11, dtype=torch.int32, device="cuda")
+    epi = C.pointer(_lib.EpilogueT(_lib.EPI_HOLES, S, time, small.data_ptr(), 10))
+    t = gu.soa(p)
+    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
+              gu.dev(B).data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
+              gu.stream())
+    ih_small = np.zeros(11, np.int32)
+    orc.calculate_ihole(gu.aos(t), ih_small, g)
+    assert small[0].item() == ih_small[0] < 0
+
+
+@pytest.mark.parametrize("gk", GRIDS)
+def test_drift_and_boundaries_bitexact(gk):
+    g = orc.Grid(**gk)
+    cg = gu.cgrid(g)
+    rng = np.random.default_rng(3)
+    n = 10000
+    p = random_particles(g, n, rng, vth=30.0)
+    exp = p.copy()
+    t = gu.soa(p)
+    orc.drift(exp, g, 0.1)
+    _lib.call("skb_drift", gu.cparts(t), n, 0.1, cg, None, gu.stream())
+    assert np.array_equal(bits(gu.aos(t)), bits(exp))
+    orc.shear_periodic_y(exp, g, -1.5, 0.7)
+    _lib.call("skb_shear_periodic_y", gu.cparts(t), n, cg, -1.5, 0.7, gu.stream())
+    assert np.array_equal(bits(gu.aos(t)), bits(exp))
+    orc.periodic_x(exp, g)
+    _lib.call("skb_periodic_x", gu.cparts(t), n, cg, gu.stream())
+    assert np.array_equal(bits(gu.aos(t)), bits(exp))
+    scratch = torch.zeros(int(_lib.load().skb_ihole_scratch_ints(n)) + 1,
+                          dtype=torch.int32, device="cuda")
+    for ntmax in (n, 10):
+        ia = np.zeros(ntmax + 1, np.int32)
+        orc.calculate_ihole(exp, ia, g)
+        ib = torch.zeros(ntmax + 1, dtype=torch.int32, device="cuda")
+        _lib.call("skb_calculate_ihole", gu.cparts(t), n, ib.data_ptr(), ntmax, cg,
+                  scratch.data_ptr(), gu.stream())
+        assert np.array_equal(ia, ib.cpu().numpy())      # same order, bit-exact
+
+
+@pytest.mark.parametrize("gk", GRIDS)
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("S", [0.0, -1.5])
+@pytest.mark.parametrize("sort", [False, True])
+def test_deposit(gk, order, S, sort):
+    if order == 2 and gk["lbx"] < 2:
+        pytest.skip("TSC needs two guard layers")
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(4)
+    n = 50000
+    p = random_particles(g, n, rng)
+    exp = g.field(orc.Float4)
+    orc.deposit(p, exp, g, order, S)
+    t = gu.soa(p)
+    til = None
+    if sort:
+        tl = gu.Tiling(g, order)
+        t = tl.sort(t, n)
+        til = tl.c()
+    cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+    _lib.call("skb_deposit", gu.cparts(t), n, cur.data_ptr(), gu.cgrid(g), order, S,
+              til, gu.stream())
+    got = gu.host(cur, orc.Float4)
+    assert rel(got, exp) < 1e-12
+    assert abs(got["t"].sum() - n) < 1e-9*n          # charge conservation
+    # cells no particle touches stay exactly zero
+    assert np.array_equal(got["t"] == 0, exp["t"] == 0)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_deposit_many_per_cell_and_empty(order):
+    """256 particles per cell (long runs in one cell) and N = 0"""
+    g = orc.Grid(nx=16, ny=16, lbx=2, lby=2)
+    rng = np.random.default_rng(5)
+    n = 16*16*256
+    p = random_particles(g, n, rng)
+    exp = g.field(orc.Float4)
+    orc.deposit(p, exp, g, order, 0.0)
+    tl = gu.Tiling(g, order)
+    t = tl.sort(gu.soa(p), n)
+    cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+    _lib.call("skb_deposit", gu.cparts(t), n, cur.data_ptr(), gu.cgrid(g), order, 0.0,
+              tl.c(), gu.stream())
+    assert rel(gu.host(cur, orc.Float4), exp) < 1e-12
+    cur.zero_()
+    _lib.call("skb_deposit", gu.cparts(t), 0, cur.data_ptr(), gu.cgrid(g), order, 0.0,
+              None, gu.stream())
+    assert float(cur.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("gk", GRIDS[:3])
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("update", [True, False])
+@pytest.mark.parametrize("sort", [False, True])
+def test_push_and_deposit(gk, order, update, sort):
+    if order == 2 and gk["lbx"] < 2:
+        pytest.skip("TSC needs two guard layers")
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(6)
+    n = 30000
+    p = random_particles(g, n, rng, vth=1.0)
+    E = random_field(g, orc.Float3, rng, -0.1, 0.1)
+    B = random_field(g, orc.Float3, rng)
+    qtmh, dt = 0.5*0.01/2, 0.01*g.dx
+    pe, ce = p.copy(), g.field(orc.Float4)
+    ie = np.zeros(n + 1, np.int32)
+    orc.push_and_deposit(pe, E, B, g, order, qtmh, dt, ie, ce, 0.0, update)
+    t = gu.soa(p)
+    til = None
+    if sort:
+        tl = gu.Tiling(g, order)
+        t = tl.sort(t, n)
+        til = tl.c()
+    cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+    ihole = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    _lib.call("skb_push_and_deposit", gu.cparts(t), n, gu.dev(E).data_ptr(),
+              gu.dev(B).data_ptr(), gu.cgrid(g), order, qtmh, dt, ihole.data_ptr(), n,
+              cur.data_ptr(), 0.0, int(update), til, gu.stream())
+    assert rel(gu.host(cur, orc.Float4), ce) < 1e-12
+    assert np.array_equal(gu.sorted_rows(gu.aos(t)), gu.sorted_rows(pe))
+    if update:
+        assert ihole[0].item() == ie[0]
+    else:
+        assert np.array_equal(gu.sorted_rows(gu.aos(t)), gu.sorted_rows(p))
+
+
+def test_push_and_deposit_cfl_flag():
+    g = orc.Grid(nx=32, ny=32)
+    rng = np.random.default_rng(7)
+    p = random_particles(g, 100, rng, vth=0.01, margin=3.0)
+    p["vx"][7] = 40.0
+    E = gu.dev(g.field(orc.Float3))
+    B = gu.dev(g.field(orc.Float3))
+    for update in (0, 1):
+        t = gu.soa(p)
+        cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+        ihole = torch.zeros(51, dtype=torch.int32, device="cuda")
+        _lib.call("skb_push_and_deposit", gu.cparts(t), 100, E.data_ptr(), B.data_ptr(),
+                  gu.cgrid(g), 1, 0.0, g.dx, ihole.data_ptr(), 50, cur.data_ptr(), 0.0,
+                  update, None, gu.stream())
+        assert ihole[0].item() == -1
+
+
+@pytest.mark.parametrize("gk", GRIDS)
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("n", [0, 1, 777, 100000])
+def test_tile_sort(gk, order, n):
+    if order == 2 and gk["lbx"] < 2:
+        pytest.skip("TSC needs two guard layers")
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(8)
+    p = random_particles(g, n, rng)
+    keys = orc.cell_keys(p, g, order, (4, 4))
+    tl = gu.Tiling(g, order)
+    t = gu.soa(p, cap=max(n, 1))
+    # integer work: keys bit-exact
+    kd = torch.zeros(max(n, 1), dtype=torch.int32, device="cuda")
+    _lib.call("skb_cell_keys", gu.cparts(t), n, gu.cgrid(g), order, 4, 4, kd.data_ptr(),
+              gu.stream())
+    assert np.array_equal(kd.cpu().numpy()[:n], keys)
+    out = tl.sort(t, n)
+    got = gu.aos(out, n)
+    # same multiset of particles, keys non-decreasing, tile offsets == bincount cumsum
+    assert np.array_equal(gu.sorted_rows(got), gu.sorted_rows(p))
+    kg = orc.cell_keys(got, g, order, (4, 4))
+    assert (np.diff(kg) >= 0).all()
+    ntiles = tl.ntx*tl.nty
+    exp_off = np.concatenate([[0], np.cumsum(np.bincount(keys >> 8, minlength=ntiles))])
+    assert np.array_equal(tl.tile_offsets.cpu().numpy(), exp_off)
+    # per-cell particle sets equal those of a stable NumPy argsort
+    ref = p[np.argsort(keys, kind="stable")]
+    kr = np.sort(keys)
+    assert np.array_equal(kg, kr)
+    if n:
+        a = np.ascontiguousarray(got).view(np.float64).reshape(-1, 5)
+        b = np.ascontiguousarray(ref).view(np.float64).reshape(-1, 5)
+        ka = np.lexsort((a[:, 1], a[:, 0], kg))
+        kb = np.lexsort((b[:, 1], b[:, 0], kr))
+        assert np.array_equal(a[ka], b[kb])
+
+
+@pytest.mark.parametrize("nmax,n,vth", [(4500, 3000, 3.0), (4000, 3900, 6.0)])
+def test_move_single_rank(nmax, n, vth):
+    """pack -> (self exchange) -> classify -> unpack == cppmove2's set and count"""
+    import skeletor_b200 as sk
+    g = orc.Grid(nx=32, ny=32)
+    rng = np.random.default_rng(9)
+    p = np.zeros(nmax, orc.Particle)
+    p[:n] = random_particles(g, n, rng, vth=vth)
+    orc.drift(p[:n], g, 0.01)
+    orc.periodic_x(p[:n], g)
+    (exp,), (nexp,) = orc.move([p], [n], [g])
+    m = sk.Manifold(32, 32, sk.COMM_SELF)
+    ions = sk.Particles(m, nmax)
+    ions._data[:, :n] = gu.soa(p[:n])
+    ions.N = n
+    ions.periodic_y()
+    assert ions.N == nexp
+    got = np.asarray(ions[:ions.N])
+    assert np.array_equal(gu.sorted_rows(got), gu.sorted_rows(exp[:nexp]))
+
+
+def test_move_unpack_compaction():
+    """more holes than arrivals: the tail is compacted into the leftover holes"""
+    n, cap = 1000, 1200
+    rng = np.random.default_rng(10)
+    p = np.zeros(n, orc.Particle)
+    for k in p.dtype.names:
+        p[k] = rng.uniform(0, 1, n)
+    holes = np.sort(rng.choice(n, 300, replace=False))
+    holes[-5:] = np.arange(n - 5, n)           # some holes in the tail itself
+    holes = np.unique(holes)
+    nh = holes.size
+    rng.shuffle(holes)                          # the fast path's list is unordered
+    nin = 120
+    inc = rng.uniform(2, 3, (nin, 5))
+    t = gu.soa(p, cap=cap)
+    ih = torch.zeros(nh + 1, dtype=torch.int32, device="cuda")
+    ih[0] = nh
+    ih[1:] = torch.as_tensor(holes + 1, dtype=torch.int32)
+    scratch = torch.zeros(2*nh + 8, dtype=torch.int32, device="cuda")
+    _lib.call("skb_move_unpack", gu.cparts(t), n, ih.data_ptr(), nh,
+              torch.as_tensor(inc, device="cuda").data_ptr(), nin, scratch.data_ptr(),
+              gu.stream())
+    newn = n + nin - nh
+    got = gu.aos(t, newn)
+    keep = np.ones(n, bool)
+    keep[holes] = False
+    exp = np.concatenate([np.ascontiguousarray(p[keep]).view(np.float64).reshape(-1, 5),
+                          inc])
+    assert np.array_equal(gu.sorted_rows(got), exp[np.lexsort(exp.T[::-1])])
+
+
+@pytest.mark.parametrize("gk", GRIDS[:2])
+@pytest.mark.parametrize("dtype", [np.float64, orc.Float3, orc.Float4])
+def test_copy_guards_bitexact(gk, dtype):
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(11)
+    if np.dtype(dtype).names is None:
+        f = rng.uniform(-1, 1, (g.myp, g.mx))
+        nc = 1
+    else:
+        f = random_field(g, dtype, rng)
+        nc = len(np.dtype(dtype).names)
+    t = gu.dev(f)
+    orc.copy_guards([f], [g])
+    _lib.call("skb_copy_guards", t.data_ptr(), nc, gu.cgrid(g), None, None, gu.stream())
+    got = t.cpu().numpy()
+    assert np.array_equal(got.ravel().view(np.uint64),
+                          np.ascontiguousarray(f).view(np.uint64).ravel())
+
+
+@pytest.mark.parametrize("gk", GRIDS[:2])
+def test_add_guards_bitexact(gk):
+    g = orc.Grid(**gk)
+    rng = np.random.default_rng(12)
+    f = random_field(g, orc.Float4, rng)
+    t = gu.dev(f)
+    orc.add_guards([f], [g])
+    cg = gu.cgrid(g)
+    _lib.call("skb_add_guards", t.data_ptr(), 4, cg, 0, None, None, gu.stream())
+    _lib.call("skb_add_guards", t.data_ptr(), 4, cg, 1, None, None, gu.stream())
+    assert np.array_equal(bits(gu.host(t, orc.Float4)), bits(f))
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_guards_multislab_emulated(nslabs):
+    """the kernels fed with 'received' rows reproduce the oracle's N-slab exchange"""
+    kw = dict(nx=32, ny=24, lbx=2, lby=2)
+    grids = [orc.Grid(rank=r, size=nslabs, **kw) for r in range(nslabs)]
+    rng = np.random.default_rng(13)
+    fs = [random_field(g, orc.Float4, rng) for g in grids]
+    ts = [gu.dev(f) for f in fs]
+
+    def pack(t, g, iy0):
+        out = torch.zeros((g.lby, g.nx, 4), dtype=torch.float64, device="cuda")
+        _lib.call("skb_pack_rows", t.data_ptr(), 4, gu.cgrid(g), iy0, g.lby,
+                  out.data_ptr(), gu.stream())
+        return out
+    # add_guards
+    exp = [f.copy() for f in fs]
+    orc.add_guards(exp, grids)
+    for t, g in zip(ts, grids):
+        _lib.call("skb_add_guards", t.data_ptr(), 4, gu.cgrid(g), 0, None, None, gu.stream())
+    ups = [pack(t, g, g.uby) for t, g in zip(ts, grids)]
+    dns = [pack(t, g, 0) for t, g in zip(ts, grids)]
+    for r, (t, g) in enumerate(zip(ts, grids)):
+        fb, fa = ups[(r - 1) % nslabs], dns[(r + 1) % nslabs]
+        _lib.call("skb_add_guards", t.data_ptr(), 4, gu.cgrid(g), 1, fb.data_ptr(),
+                  fa.data_ptr(), gu.stream())
+    for t, e in zip(ts, exp):
+        assert np.array_equal(bits(gu.host(t, orc.Float4)), bits(e))
+    # copy_guards
+    orc.copy_guards(exp, grids)
+    ups = [pack(t, g, g.uby - g.lby) for t, g in zip(ts, grids)]
+    dns = [pack(t, g, g.lby) for t, g in zip(ts, grids)]
+    for r, (t, g) in enumerate(zip(ts, grids)):
+        fb, fa = ups[(r - 1) % nslabs], dns[(r + 1) % nslabs]
+        _lib.call("skb_copy_guards", t.data_ptr(), 4, gu.cgrid(g), fb.data_ptr(),
+                  fa.data_ptr(), gu.stream())
+    for t, e in zip(ts, exp):
+        assert np.array_equal(bits(gu.host(t, orc.Float4)), bits(e))
+
+
+@pytest.mark.parametrize("gk", GRIDS)
+def test_finite_differences_bitexact(gk):
+    g = orc.Grid(**gk)
+    cg = gu.cgrid(g)
+    rng = np.random.default_rng(14)
+    f = random_field(g, orc.Float3, rng)
+    s = rng.uniform(0.5, 1.5, (g.myp, g.mx))
+    tf, ts = gu.dev(f), gu.dev(s)
+    px, py, pz = tf.data_ptr(), tf.data_ptr() + 8, tf.data_ptr() + 16
+    st = gu.stream()
+
+    def out3():
+        return torch.zeros((g.myp, g.mx, 3), dtype=torch.float64, device="cuda")
+    e = g.field(orc.Float3)
+    orc.gradient(s, e, g)
+    o = out3()
+    _lib.call("skb_gradient", ts.data_ptr(), 1, o.data_ptr(), cg, st)
+    assert np.array_equal(bits(gu.host(o, orc.Float3)), bits(e))
+    for down in (True, False):
+        e = g.field(orc.Float3)
+        orc.curl(f, e, g, down=down)
+        o = out3()
+        _lib.call("skb_curl", px, py, pz, 3, o.data_ptr(), cg, int(down), st)
+        assert np.array_equal(bits(gu.host(o, orc.Float3)), bits(e))
+    for up, fn in ((0, orc.unstagger), (1, orc.stagger)):
+        e = g.field(orc.Float3)
+        fn(f, e, g)
+        o = out3()
+        _lib.call("skb_interp", px, py, pz, 3, o.data_ptr(), cg, up, st)
+        assert np.array_equal(bits(gu.host(o, orc.Float3)), bits(e))
+    e = g.field()
+    orc.divergence(f, e, g)
+    o = torch.zeros((g.myp, g.mx), dtype=torch.float64, device="cuda")
+    _lib.call("skb_divergence", px, py, 3, o.data_ptr(), cg, st)
+    assert np.array_equal(bits(o.cpu().numpy()), bits(e))
+
+
+@pytest.mark.parametrize("gk", GRIDS[:2])
+def test_ohm_and_faraday(gk):
+    g = orc.Grid(**gk)
+    cg = gu.cgrid(g)
+    rng = np.random.default_rng(15)
+    src = random_field(g, orc.Float4, rng)
+    src["t"] = rng.uniform(0.5, 1.5, (g.myp, g.mx))
+    B = random_field(g, orc.Float3, rng)
+    orc.copy_guards([src], [g])
+    orc.copy_guards([B], [g])
+    E = g.field(orc.Float3)
+    Je, Bc = orc.ohm(src, B, E, g, charge=1.3, temperature=0.7, eta=0.05)
+    tE = torch.zeros((g.myp, g.mx, 3), dtype=torch.float64, device="cuda")
+    tJ, tB = torch.zeros_like(tE), torch.zeros_like(tE)
+    _lib.call("skb_ohm", gu.dev(src).data_ptr(), gu.dev(B).data_ptr(), tE.data_ptr(),
+              tJ.data_ptr(), tB.data_ptr(), cg, 0.7/1.3, 0.05, gu.stream())
+    a = (slice(g.lby, g.uby), slice(g.lbx, g.ubx))
+    assert rel(gu.host(tE, orc.Float3)[a], E[a]) < 1e-12
+    assert np.array_equal(bits(gu.host(tB, orc.Float3)[a]), bits(Bc[a]))
+    assert np.array_equal(bits(gu.host(tJ, orc.Float3)[a]), bits(Je[a]))
+    # Faraday: bit-exact
+    orc.copy_guards([E], [g])
+    tEe, tBb = gu.dev(E), gu.dev(B)
+    orc.faraday(E, B, g, 0.01)
+    _lib.call("skb_faraday", tEe.data_ptr(), tBb.data_ptr(), None, cg, 0.01, gu.stream())
+    assert np.array_equal(bits(gu.host(tBb, orc.Float3)[a]), bits(B[a]))

@@ -46,13 +46,14 @@ def test_push_bitexact(gk, order, modified, sort):
     exp = p.copy()
     orc.push(exp, E, B, g, order, qtmh, dt, modified, Omega, S)
     t = gu.soa(p)
+    tE, tB = gu.dev(E), gu.dev(B)
     til = None
     if sort:
         tl = gu.Tiling(g, order)
         t = tl.sort(t, n)
         til = tl.c()
-    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
-              gu.dev(B).data_ptr(), gu.cgrid(g), order, qtmh, dt, int(modified), Omega,
+    _lib.call("skb_boris_push", gu.cparts(t), n, tE.data_ptr(),
+              tB.data_ptr(), gu.cgrid(g), order, qtmh, dt, int(modified), Omega,
               S, til, None, gu.stream())
     got = gu.aos(t)
     if sort:
@@ -80,11 +81,12 @@ def test_push_epilogue_matches_reference_sequence(gk, shear):
     orc.calculate_ihole(exp, ih_exp, g)
     orc.periodic_x(exp, g)
     t = gu.soa(p)
+    tE, tB = gu.dev(E), gu.dev(B)
     ihole = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
     flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X | (_lib.EPI_SHEAR if shear else 0)
     epi = C.pointer(_lib.EpilogueT(flags, S, time, ihole.data_ptr(), n))
-    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
-              gu.dev(B).data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
+    _lib.call("skb_boris_push", gu.cparts(t), n, tE.data_ptr(),
+              tB.data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
               gu.stream())
     assert np.array_equal(bits(gu.aos(t)), bits(exp))
     ih = ihole.cpu().numpy()
@@ -94,8 +96,8 @@ def test_push_epilogue_matches_reference_sequence(gk, shear):
     small = torch.zeros(11, dtype=torch.int32, device="cuda")
     epi = C.pointer(_lib.EpilogueT(_lib.EPI_HOLES, S, time, small.data_ptr(), 10))
     t = gu.soa(p)
-    _lib.call("skb_boris_push", gu.cparts(t), n, gu.dev(E).data_ptr(),
-              gu.dev(B).data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
+    _lib.call("skb_boris_push", gu.cparts(t), n, tE.data_ptr(),
+              tB.data_ptr(), gu.cgrid(g), 1, qtmh, dt, 0, 0.0, 0.0, None, epi,
               gu.stream())
     ih_small = np.zeros(11, np.int32)
     orc.calculate_ihole(gu.aos(t), ih_small, g)
@@ -206,8 +208,9 @@ def test_push_and_deposit(gk, order, update, sort):
         til = tl.c()
     cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
     ihole = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
-    _lib.call("skb_push_and_deposit", gu.cparts(t), n, gu.dev(E).data_ptr(),
-              gu.dev(B).data_ptr(), gu.cgrid(g), order, qtmh, dt, ihole.data_ptr(), n,
+    tE, tB = gu.dev(E), gu.dev(B)
+    _lib.call("skb_push_and_deposit", gu.cparts(t), n, tE.data_ptr(),
+              tB.data_ptr(), gu.cgrid(g), order, qtmh, dt, ihole.data_ptr(), n,
               cur.data_ptr(), 0.0, int(update), til, gu.stream())
     assert rel(gu.host(cur, orc.Float4), ce) < 1e-12
     assert np.array_equal(gu.sorted_rows(gu.aos(t)), gu.sorted_rows(pe))
@@ -312,9 +315,9 @@ def test_move_unpack_compaction():
     ih[0] = nh
     ih[1:] = torch.as_tensor(holes + 1, dtype=torch.int32)
     scratch = torch.zeros(2*nh + 8, dtype=torch.int32, device="cuda")
+    tinc = torch.as_tensor(inc, device="cuda")
     _lib.call("skb_move_unpack", gu.cparts(t), n, ih.data_ptr(), nh,
-              torch.as_tensor(inc, device="cuda").data_ptr(), nin, scratch.data_ptr(),
-              gu.stream())
+              tinc.data_ptr(), nin, scratch.data_ptr(), gu.stream())
     newn = n + nin - nh
     got = gu.aos(t, newn)
     keep = np.ones(n, bool)
@@ -446,7 +449,8 @@ def test_ohm_and_faraday(gk):
     Je, Bc = orc.ohm(src, B, E, g, charge=1.3, temperature=0.7, eta=0.05)
     tE = torch.zeros((g.myp, g.mx, 3), dtype=torch.float64, device="cuda")
     tJ, tB = torch.zeros_like(tE), torch.zeros_like(tE)
-    _lib.call("skb_ohm", gu.dev(src).data_ptr(), gu.dev(B).data_ptr(), tE.data_ptr(),
+    tsrc, tB0 = gu.dev(src), gu.dev(B)
+    _lib.call("skb_ohm", tsrc.data_ptr(), tB0.data_ptr(), tE.data_ptr(),
               tJ.data_ptr(), tB.data_ptr(), cg, 0.7/1.3, 0.05, gu.stream())
     a = (slice(g.lby, g.uby), slice(g.lbx, g.ubx))
     assert rel(gu.host(tE, orc.Float3)[a], E[a]) < 1e-12

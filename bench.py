@@ -1,0 +1,329 @@
+"""bench.py — float64 particle-steps/s of the skeletor particle hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+One STEP = one pass of the hot path over all particles of the workload:
+    ions.push(E, B, dt)  ->  sources.deposit(ions)  ->  sources.add_guards()
+    ->  sources.copy_guards()
+(the loop body of reference tests/test_ionacoustic.py:160-178 without Ohm;
+SURVEY.md §8d), i.e. gather + Boris push + fused boundary epilogue + migration +
+tile sort + deposit + guard cells.  One particle-step = one particle through that.
+
+Workload (BASELINE.json config 5, the one the metric/target is quoted on): uniform
+Maxwellian plasma, 2048 x 2048 grid x 256 particles/cell = 1.07e9 particles, CIC,
+vt*dt/dx = 0.1, smooth E ~ 0.01, B = z-hat, float64, synthetic (torch.Generator
+seed 1234 + rank).  STRONG scaling: the grid is split into N y-slabs, one per GPU.
+
+JSON keys beyond the base contract:
+  roofline     dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), from CUDA
+               events around that kernel in an instrumented pass (not the timed one)
+  kernels      the same for every kernel of the step
+  cpu_baseline the unmodified reference's compiled kernels (oracle/_ref) on the
+               box's host cores, bounded sample (rank 0, N = 1 only)
+  e2e          same step driven with HOST field buffers: E,B copied H2D from pinned
+               memory and the sources read back D2H every step
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "float64 particle-steps/sec"
+UNIT = "particle-steps/s"
+NX = NY = 2048
+PPC = 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=NX)
+    ap.add_argument("--ny", type=int, default=NY)
+    ap.add_argument("--ppc", type=int, default=PPC)
+    ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {"workload": "uniform Maxwellian plasma %dx%d grid x %d ppc (BASELINE config 5), "
+                       "push+deposit+add_guards+copy_guards per step" % (a.nx, a.ny, a.ppc),
+           "grid": [a.nx, a.ny], "ppc": a.ppc, "particles": a.nx*a.ny*a.ppc,
+           "interpolation": "CIC" if a.order == 1 else "TSC",
+           "decomposition": "y-slabs, 1 per GPU", "vt_dt_over_dx": 0.1,
+           "l2_policy": "inputs larger than L2 (>= 5 GB of particle data per GPU)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------
+def reference_arm(a):
+    """--impl reference: the reference's own CPU implementation on the host cores,
+    every step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_driver
+    rows = 8
+    r = ref_driver.measure(nx=a.nx, rows=rows, ppc=a.ppc, steps=a.steps,
+                           warmup=min(a.warmup, 1))
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": workload_config(a, {"sample": r["sample"]}),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+                             "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def b200_arm(a):
+    import numpy as np
+    import torch
+    import skeletor_b200 as sk
+    from skeletor_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    comm = sk.COMM_WORLD if world > 1 else sk.COMM_SELF
+    rank, size = comm.rank, comm.size
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    m = sk.Manifold(a.nx, a.ny, comm, lbx=1 if a.order == 1 else 2,
+                    lby=1 if a.order == 1 else 2, Lx=1.0, Ly=a.ny/a.nx)
+    n_local = a.nx*m.nyp*a.ppc
+    n_total = a.nx*a.ny*a.ppc
+    nmax = int(1.05*n_local) + 4096
+    ions = sk.Particles(m, nmax, charge=1.0, mass=1.0, order=a.order,
+                        nbmax=max(n_local//100, 1 << 16))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    d = ions._data
+    d[0, :n_local] = torch.rand(n_local, generator=gen, device=dev, dtype=torch.float64)*a.nx
+    d[1, :n_local] = m.noff + torch.rand(n_local, generator=gen, device=dev,
+                                         dtype=torch.float64)*m.nyp
+    d[2:5, :n_local] = torch.randn((3, n_local), generator=gen, device=dev,
+                                   dtype=torch.float64)
+    ions.N = n_local
+    dt = 0.1*m.dx       # vt = 1  ->  vt*dt/dx = 0.1
+    E = sk.Field(m, dtype=sk.Float3)
+    B = sk.Field(m, dtype=sk.Float3)
+    xg, yg = np.meshgrid(m.x, m.y)
+    E['x'].active = 0.01*np.sin(2*np.pi*xg/m.Lx)
+    E['y'].active = 0.01*np.cos(2*np.pi*yg/m.Ly)
+    B['z'].active = 1.0
+    E.copy_guards()
+    B.copy_guards()
+    src = sk.Sources(m)
+
+    def step():
+        ions.push(E, B, dt)
+        src.deposit(ions)
+        src.add_guards()
+        src.copy_guards()
+
+    def barrier():
+        if size > 1:
+            comm.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if size > 1:
+            ms = comm.allreduce(ms, op=sk.comm.MAX)
+        return ms
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    k0 = _lib.kernel_launches
+    ms = timed(step, a.steps)
+    launches = _lib.kernel_launches - k0
+    clk = clocks.stop() if rank == 0 else None
+    value = n_total*a.steps/(ms*1e-3)
+
+    # ---- per-kernel roofline: instrumented pass, CUDA events around each C-ABI call
+    peak, peak_src = measured_peak()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc = {"push": [], "migrate": [], "tile_sort": [], "deposit": [], "guards": []}
+    for _ in range(3):
+        t = [ev() for _ in range(6)]
+        torch.cuda.synchronize()
+        t[0].record(); ions._push_kernel(E, B, dt, False)
+        t[1].record(); ions.move()
+        t[2].record(); ions.sort()
+        t[3].record()
+        src.t.zero_()
+        ions._ensure_sorted()
+        _lib.call("skb_deposit", ions._c, ions.N, src.ptr, m.c, ions.order, 0.0,
+                  ions._tiling_c(), torch.cuda.current_stream().cuda_stream)
+        t[4].record()
+        src.boundaries_set = False
+        src.normalize(ions); src.add_guards(); src.copy_guards()
+        t[5].record()
+        torch.cuda.synchronize()
+        for name, i in zip(acc, range(5)):
+            acc[name].append(t[i].elapsed_time(t[i + 1]))
+    npart = ions.N
+    cells = m.mx*m.myp
+    # algorithmic bytes per launch: push 80 B/particle + E,B tiles
+    # 48 B/cell; deposit 40 B/particle + 32 B/cell; sort: 16 B (keys) + 80 B (move)
+    alg = {"push": 80.0*npart + 48.0*cells, "deposit": 40.0*npart + 32.0*cells,
+           "tile_sort": 96.0*npart}
+    kern = {}
+    for name, ts in acc.items():
+        tmin = min(ts)
+        kern[name] = {"ms": round(tmin, 4)}
+        if name in alg:
+            gbs = alg[name]/(tmin*1e-3)/1e9
+            kern[name].update({"alg_bytes": alg[name], "achieved_gbs": round(gbs, 1),
+                               "frac": round(gbs/peak, 4)})
+    step_ms = sum(v["ms"] for v in kern.values())
+    for v in kern.values():
+        v["share"] = round(v["ms"]/step_ms, 4)
+    dom = max(("push", "deposit", "tile_sort"), key=lambda k: kern[k]["ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"],
+                "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
+                "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": kern[dom]["alg_bytes"],
+                "ms_per_launch": kern[dom]["ms"]}
+    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(dom)
+        except Exception:
+            pass
+
+    # ---- e2e: host field buffers in, host sources out, every step
+    e2e = None
+    if not a.no_e2e:
+        hE = torch.empty(E.t.shape, dtype=torch.float64).pin_memory()
+        hB = torch.empty(B.t.shape, dtype=torch.float64).pin_memory()
+        hS = torch.empty(src.t.shape, dtype=torch.float64).pin_memory()
+        hE.copy_(E.t); hB.copy_(B.t)
+
+        def step_e2e():
+            E.t.copy_(hE, non_blocking=True)
+            B.t.copy_(hB, non_blocking=True)
+            step()
+            hS.copy_(src.t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(2):
+            step_e2e()
+        ms2 = timed(step_e2e, a.steps)
+        e2e = {"value": n_total*a.steps/(ms2*1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(hE.numel()*8 + hB.numel()*8),
+               "d2h_bytes_per_step": int(hS.numel()*8), "ms_per_step": ms2/a.steps,
+               "what": "E,B copied H2D from pinned host memory and sources copied D2H "
+                       "inside the timed step; particles stay resident in HBM"}
+
+    cpu = None
+    if rank == 0 and size == 1 and not a.no_cpu_baseline:
+        from oracle import ref_driver
+        cpu = ref_driver.measure(nx=a.nx, rows=8, ppc=a.ppc, steps=6, warmup=1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms/a.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": workload_config(a, {"particles_per_gpu": n_local}),
+                "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clk, "impl": "b200"}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

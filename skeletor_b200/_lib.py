@@ -81,7 +81,11 @@ OTHER = {
 }
 
 _lib = None
-launches = 0   # number of C-ABI calls made (bench.py reports kernel launches from it)
+launches = 0          # number of C-ABI calls made
+kernel_launches = 0   # CUDA kernels those calls launched (bench.py's gpu_launches)
+
+# kernels launched per C-ABI call (memsets are not counted)
+KERNELS_PER_CALL = {"skb_tile_sort": 6, "skb_calculate_ihole": 3, "skb_move_unpack": 3}
 
 
 class SkeletorCudaError(RuntimeError):
@@ -112,10 +116,11 @@ def load():
 
 def call(name, *args):
     """Invoke a C-ABI entry point, raising on a CUDA error."""
-    global launches
+    global launches, kernel_launches
     lib = load()
     rc = getattr(lib, name)(*args)
     launches += 1
+    kernel_launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.skb_error_string(rc)
         raise SkeletorCudaError("%s failed: CUDA error %d (%s)" % (

@@ -68,7 +68,10 @@ class Particles:
     """Container class for particles in a given subdomain"""
 
     def __init__(self, manifold, Nmax,
-                 time=0.0, charge=1.0, mass=1.0, n0=1.0, order=1):
+                 time=0.0, charge=1.0, mass=1.0, n0=1.0, order=1, nbmax=None):
+        """Same signature as the reference (particles.py:10-11) plus `nbmax`: the
+        reference always sizes the exchange buffers as 0.1*Nmax (particles.py:22),
+        which is tens of GB at 1e9 particles; nbmax overrides that."""
         _lib.require_cuda()
         msg = 'Interpolation order {} needs more guard layers'.format(order)
         # The number of guard layers on each side needs to be equal to
@@ -77,7 +80,7 @@ class Particles:
 
         Nmax = int(Nmax)
         # Size of buffer for passing particles between processors
-        nbmax = int(max(0.1*Nmax, 1))
+        nbmax = int(max(0.1*Nmax, 1)) if nbmax is None else int(max(nbmax, 1))
         # Size of ihole buffer for particles leaving processor
         ntmax = 2*nbmax
         self.nbmax, self.ntmax = nbmax, ntmax
@@ -314,6 +317,11 @@ class Particles:
         self.periodic_y()
 
     def _push(self, E, B, dt, modified):
+        self._push_kernel(E, B, dt, modified)
+        self.move()
+        self.sort()
+
+    def _push_kernel(self, E, B, dt, modified):
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
@@ -332,8 +340,6 @@ class Particles:
                   float(getattr(m, 'S', 0.0)) if modified else 0.0,
                   self._tiling_c(), self._epilogue(flags, getattr(m, 'S', 0.0)),
                   _stream())
-        self.move()
-        self.sort()
 
     def push(self, E, B, dt):
         """A standard Boris push which updates positions and velocities

@@ -58,6 +58,9 @@ typedef struct {
 typedef struct {
   const int *tile_offsets;     /* [ntx*nty + 1] first particle of each tile */
   const int *chunk_first_tile; /* [ceil(n_sorted/chunk)] tile of particle c*chunk */
+  const int *cell_end;         /* [ncells] end of each cell's particle range (cell k =
+                                  [cell_end[k-1], cell_end[k])), or NULL.  Lets the
+                                  deposit give every warp whole cells. */
   int ntx, nty, tlx, tly;
   int chunk;                   /* particles per CTA work item */
   long long n_sorted;

@@ -27,7 +27,7 @@ class ParticlesT(C.Structure):
 
 class TilingT(C.Structure):
     _fields_ = [("tile_offsets", c_vp), ("chunk_first_tile", c_vp),
-                ("ntx", c_int), ("nty", c_int), ("tlx", c_int), ("tly", c_int),
+                ("cell_end", c_vp), ("ntx", c_int), ("nty", c_int), ("tlx", c_int), ("tly", c_int),
                 ("chunk", c_int), ("n_sorted", c_ll)]
 
 

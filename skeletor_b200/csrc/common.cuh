@@ -37,6 +37,7 @@ static inline DevGrid make_grid(const skb_grid_t *g) {
 struct DevTiling {
   const int *tile_offsets;
   const int *chunk_first_tile;
+  const int *cell_end;
   int ntx, nty, tlx, tly, chunk;
   long long n_sorted;
 };
@@ -45,10 +46,11 @@ static inline DevTiling make_tiling(const skb_tiling_t *t) {
   DevTiling d;
   if (t && t->tile_offsets) {
     d.tile_offsets = t->tile_offsets; d.chunk_first_tile = t->chunk_first_tile;
+    d.cell_end = t->cell_end;
     d.ntx = t->ntx; d.nty = t->nty; d.tlx = t->tlx; d.tly = t->tly;
     d.chunk = t->chunk; d.n_sorted = t->n_sorted;
   } else {
-    d.tile_offsets = nullptr; d.chunk_first_tile = nullptr;
+    d.tile_offsets = nullptr; d.chunk_first_tile = nullptr; d.cell_end = nullptr;
     d.ntx = d.nty = 1; d.tlx = d.tly = 4; d.chunk = 2048; d.n_sorted = 0;
   }
   return d;

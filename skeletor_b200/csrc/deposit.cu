@@ -264,6 +264,103 @@ deposit_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Cell-aligned deposit (the fast path when the ordering is exact and cell_end is
+// known): every warp is handed WHOLE cells, so all 32 lanes accumulate the same
+// stencil in registers for the whole cell and there is exactly one warp reduction
+// (butterfly over lanes) and one emit per cell.  Loads are issued UNR iterations
+// ahead of their use to keep enough bytes in flight with only 16 resident warps.
+// A particle whose stencil base is not the cell it is filed under (caller passed a
+// stale ordering) is deposited on its own through HBM atomics: correct, just slow.
+#define DEP_UNR 4
+
+template <int NS>
+__device__ __forceinline__ void single_particle_emit(const double (&wx)[NS],
+                                                     const double (&wy)[NS], int ix, int iy,
+                                                     double vxr, double vy, double vz,
+                                                     double *__restrict__ cur,
+                                                     const DevGrid &g) {
+  const int lo = (NS == 3) ? 1 : 0;
+  const int x_lo = ix - lo, y_lo = iy - lo;
+  if (!(x_lo >= 0 && x_lo + NS <= g.mx && y_lo >= 0 && y_lo + NS <= g.myp)) return;
+  double *b = cur + ((size_t)y_lo * g.mx + x_lo) * 4;
+#pragma unroll
+  for (int r = 0; r < NS; r++)
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+      const double wgt = wy[r] * wx[c];
+      double *v = b + ((size_t)r * g.mx + c) * 4;
+      atomicAdd(v + 0, wgt);
+      atomicAdd(v + 1, wgt * vxr);
+      atomicAdd(v + 2, wgt * vy);
+      atomicAdd(v + 3, wgt * vz);
+    }
+}
+
+template <int ORDER>
+__global__ void __launch_bounds__(DEP_THREADS)
+deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
+                     DepParams q, int parts, int wstride, int wrows) {
+  constexpr int NS = ORDER + 1;
+  extern __shared__ double sw[];
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;          // cells per CTA
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const int pbeg = c0 ? tl.cell_end[c0 - 1] : 0;
+  const int pend = tl.cell_end[c0 + cpp - 1];
+  if (pbeg == pend) return;                            // uniform: no particles here
+  const Window w = tile_window(tile, tl, g);
+  zero_window(sw, wstride * wrows * 4);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
+  for (int cell = c0 + wv; cell < c0 + cpp; cell += DEP_THREADS / 32) {
+    const int s = cell ? tl.cell_end[cell - 1] : 0;
+    const int e = tl.cell_end[cell];
+    if (s == e) continue;
+    const int local = cell & ((1 << cells_log2) - 1);
+    Acc<NS> a;
+#pragma unroll
+    for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+    a.ix = bx + (local & ((1 << tl.tlx) - 1));
+    a.iy = by + (local >> tl.tlx);
+    for (int base = s; base < e; base += 32 * DEP_UNR) {
+      double x[DEP_UNR], y[DEP_UNR], vx[DEP_UNR], vy[DEP_UNR], vz[DEP_UNR];
+#pragma unroll
+      for (int u = 0; u < DEP_UNR; u++) {
+        const int i = base + u * 32 + lane;
+        if (i < e) { x[u] = P.x[i]; y[u] = P.y[i]; vx[u] = P.vx[i]; vy[u] = P.vy[i]; vz[u] = P.vz[i]; }
+      }
+#pragma unroll
+      for (int u = 0; u < DEP_UNR; u++) {
+        const int i = base + u * 32 + lane;
+        if (i < e) {
+          double xs = x[u] + q.offx, ys = y[u] + q.offy;
+          if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+          int ix, iy;
+          double wx[NS], wy[NS];
+          particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+          // particle velocity relative to the background shear, deposit.pxd:24
+          const double vxr = vx[u] + q.S * (y[u] * g.dy + g.y0);
+          if (ix == a.ix && iy == a.iy) accumulate<ORDER>(a, wx, wy, vxr, vy[u], vz[u]);
+          else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy[u], vz[u], cur, g);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS * NS * 4; i++) {
+      double t = a.v[i];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) t += __shfl_down_sync(SKB_FULL, t, d);
+      a.v[i] = t;
+    }
+    if (lane == 0) emit<NS>(a, sw, w, wstride, cur, g);
+  }
+  __syncthreads();
+  flush_window(sw, w, wstride, cur, g);
+}
+
 // decode ihole[0] = count | CFL bit into the reference's in-band convention
 __global__ void finalize_fused_ihole_kernel(int *ihole, int ntmax) {
   int v = ihole[0];
@@ -307,9 +404,29 @@ extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
   q.offy = g.lby - 0.5 - g.noff;
   q.S = S;
   FusedParams fq = {};
+  if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
+  if (tl.tile_offsets && tl.cell_end && tl.n_sorted > 0) {
+    // exact ordering with per-cell ranges: whole cells per warp
+    const int ntiles = tl.ntx * tl.nty;
+    const int cells = 1 << (tl.tlx + tl.tly);
+    int parts = 1;
+    while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
+    const int ws = window_stride(tl), wr = window_rows(tl);
+    const size_t smem = (size_t)ws * wr * 4 * sizeof(double);
+    if (order == 1)
+      deposit_cells_kernel<1><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
+    else
+      deposit_cells_kernel<2><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
+    SKB_CHECK_LAUNCH();
+    if (np <= tl.n_sorted) return 0;
+    // unsorted tail [n_sorted, np): generic kernel without ordering
+    const long long n0 = tl.n_sorted;
+    p.x += n0; p.y += n0; p.vx += n0; p.vy += n0; p.vz += n0;
+    np -= n0;
+    tl = make_tiling(nullptr);
+  }
   if (order == 1) return launch_deposit<1, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
-  if (order == 2) return launch_deposit<2, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
-  return (int)cudaErrorInvalidValue;
+  return launch_deposit<2, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
 }
 
 extern "C" int skb_push_and_deposit(skb_particles_t p, long long np, const double *E,

@@ -18,6 +18,13 @@
 #include "gather.cuh"
 
 #define PUSH_THREADS 256
+#ifndef PUSH_PREFETCH
+#define PUSH_PREFETCH 2
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 struct PushParams {
   KickParams k;
@@ -47,6 +54,20 @@ __device__ __forceinline__ void boundary_epilogue(const PushParams &q, const Dev
   if (q.flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, (double)g.nx);
 }
 
+// gather + kick + drift + boundary epilogue for one particle
+template <int ORDER, bool MODIFIED>
+__device__ __forceinline__ void push_one(const double *sE, const double *sB, const Window &w,
+                                         int wstride, const double *E, const double *B,
+                                         const DevGrid &g, const PushParams &q, long long i,
+                                         double &x, double &y, double &vx, double &vy,
+                                         double &vz) {
+  fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
+  // drift_particle, particle_push.pxd:88-91
+  x = x + vx * q.dtdsx;
+  y = y + vy * q.dtdsy;
+  if (q.flags) boundary_epilogue(q, g, i, x, y, vx);
+}
+
 template <int ORDER, bool MODIFIED>
 __global__ void __launch_bounds__(PUSH_THREADS)
 push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
@@ -69,12 +90,15 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
       __syncthreads();
     }
     for (long long i = s0 + threadIdx.x; i < s1; i += PUSH_THREADS) {
+      // pull the lines of the particle this thread handles PF iterations from now
+      // into L2: more DRAM requests in flight at no register cost
+      const long long ip = i + PUSH_PREFETCH * PUSH_THREADS;
+      if (ip < s1) {
+        prefetch_l2(P.x + ip); prefetch_l2(P.y + ip); prefetch_l2(P.vx + ip);
+        prefetch_l2(P.vy + ip); prefetch_l2(P.vz + ip);
+      }
       double x = P.x[i], y = P.y[i], vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
-      fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
-      // drift_particle, particle_push.pxd:88-91
-      x = x + vx * q.dtdsx;
-      y = y + vy * q.dtdsy;
-      if (q.flags) boundary_epilogue(q, g, i, x, y, vx);
+      push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
       P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
     }
   }

@@ -185,6 +185,7 @@ class Particles:
             return None
         return C.pointer(_lib.TilingT(
             self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(),
+            self._cell_counts.data_ptr(),
             self._ntx, self._nty, TLX, TLY, CHUNK, self._n_sorted))
 
     def _epilogue(self, flags, S=0.0):

@@ -73,6 +73,7 @@ class Tiling:
         self.tile_offsets = torch.zeros(nt + 1, **i32)
         self.chunk_first = None
         self.n = 0
+        self.use_cells = True
 
     def sort(self, t, n):
         out = torch.zeros_like(t)
@@ -86,7 +87,9 @@ class Tiling:
 
     def c(self):
         return C.pointer(_lib.TilingT(self.tile_offsets.data_ptr(),
-                                      self.chunk_first.data_ptr(), self.ntx, self.nty,
+                                      self.chunk_first.data_ptr(),
+                                      self.cell_counts.data_ptr() if self.use_cells else None,
+                                      self.ntx, self.nty,
                                       self.tlx, self.tly, self.chunk, self.n))
 
 

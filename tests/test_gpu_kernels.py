@@ -462,3 +462,32 @@ def test_ohm_and_faraday(gk):
     orc.faraday(E, B, g, 0.01)
     _lib.call("skb_faraday", tEe.data_ptr(), tBb.data_ptr(), None, cg, 0.01, gu.stream())
     assert np.array_equal(bits(gu.host(tBb, orc.Float3)[a]), bits(B[a]))
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_deposit_stale_ordering_and_tail(order):
+    """the ordering is a performance hint only: deposit stays correct when the
+    particles moved after the sort, and when an unsorted tail follows the sorted range"""
+    g = orc.Grid(nx=64, ny=32, lbx=2, lby=2)
+    rng = np.random.default_rng(21)
+    n, ntail = 40000, 3000
+    p = random_particles(g, n + ntail, rng, margin=1.0)
+    tl = gu.Tiling(g, order)
+    t = gu.soa(p)
+    srt = tl.sort(t[:, :n].contiguous(), n)
+    full = torch.cat([srt, t[:, n:]], dim=1).contiguous()
+    # move every particle by up to +-0.8 cells AFTER the sort, keep the stale tiling
+    full[0] += torch.as_tensor(rng.uniform(-0.8, 0.8, n + ntail), device="cuda")
+    full[1] += torch.as_tensor(rng.uniform(-0.8, 0.8, n + ntail), device="cuda")
+    exp = g.field(orc.Float4)
+    orc.deposit(gu.aos(full), exp, g, order, 0.0)
+    cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+    _lib.call("skb_deposit", gu.cparts(full), n + ntail, cur.data_ptr(), gu.cgrid(g),
+              order, 0.0, tl.c(), gu.stream())
+    assert rel(gu.host(cur, orc.Float4), exp) < 1e-12
+    # same through the run-based kernel (no per-cell ranges)
+    tl.use_cells = False
+    cur.zero_()
+    _lib.call("skb_deposit", gu.cparts(full), n + ntail, cur.data_ptr(), gu.cgrid(g),
+              order, 0.0, tl.c(), gu.stream())
+    assert rel(gu.host(cur, orc.Float4), exp) < 1e-12

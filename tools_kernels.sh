@@ -1,0 +1,10 @@
+#!/bin/bash
+# prints value, ms/step and per-kernel ms / frac from a short bench run
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>&1 | tail -3 | python -c "
+import sys, json
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d = json.loads(ln); print('value %.4g  ms/step %.2f' % (d['value'], d['ms_per_step']))
+        for k, v in d['kernels'].items(): print('  %-10s %8.3f ms  frac %s' % (k, v['ms'], v.get('frac')))
+    else: print(ln.rstrip())
+"

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libskeletor_b200.so")
+LIB_PATH = os.environ.get("SKELETOR_B200_LIB") or \
+    os.path.join(_HERE, "lib", "libskeletor_b200.so")
 
 c_int, c_ll, c_dbl, c_vp = C.c_int, C.c_longlong, C.c_double, C.c_void_p
 

@@ -19,7 +19,7 @@
 
 #define PUSH_THREADS 256
 #ifndef PUSH_PREFETCH
-#define PUSH_PREFETCH 2
+#define PUSH_PREFETCH 1
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {

@@ -1,0 +1,84 @@
+"""Multi-rank parity check, launched under torchrun (one process per GPU, NCCL):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py
+
+Runs the golden scenarios of tests/scenarios.py on N y-slabs and checks, on rank 0,
+the reference's own invariant "N ranks == 1 rank" (reference
+tests/test_skeletor.py:142-150) against the single-rank golden fixtures: particle
+count exact, sorted particle coordinates and active-cell fields <= 1e-12 relative.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import scenarios as sc  # noqa: E402
+
+
+def rows(p):
+    a = np.ascontiguousarray(p).view(np.float64).reshape(-1, 5)
+    return a[np.lexsort((a[:, 4], a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def main():
+    import skeletor_b200 as sk
+    from skeletor_b200.time_steppers.horowitz import TimeStepper as Horowitz
+    from skeletor_b200.time_steppers.predictor_corrector import TimeStepper as PC
+    comm = sk.comm.init_world()
+    ns = types.SimpleNamespace(
+        Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
+        Particles=sk.Particles, Sources=sk.Sources, Field=sk.Field, Ohm=sk.Ohm,
+        Faraday=sk.Faraday, State=sk.State, Float3=sk.Float3, comm=comm,
+        HorowitzStepper=Horowitz, PredictorCorrectorStepper=PC)
+    names = ["ionacoustic_cic", "ionacoustic_tsc", "gyro_cic", "gyro_tsc", "sheared_cic",
+             "sheared_tsc", "predictor_corrector_tsc", "horowitz_cic"]
+    lb = {"ionacoustic_cic": 1}
+    failed = 0
+    for name in names:
+        gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = sc.SCENARIOS[name](ns)
+        # gather the slabs on every rank (object allgather: diagnostics path)
+        parts = np.concatenate(comm.allgather(res["particles"]))
+        ntot = comm.allreduce(int(res["N"]))
+        g = lb.get(name, 2)
+        rtol = 1e-10 if ("horowitz" in name or "predictor" in name) else 1e-12
+        errs = {}
+        ok = ntot == int(gold["N"])
+        e = np.abs(rows(parts) - rows(gold["particles"])).max() / \
+            np.abs(rows(gold["particles"])).max()
+        errs["particles"] = e
+        ok &= e <= rtol
+        for key in gold.files:
+            if key in ("N", "particles", "time", "t"):
+                continue
+            act = np.concatenate(comm.allgather(
+                np.ascontiguousarray(res[key][g:-g, g:-g])))
+            ref = np.ascontiguousarray(gold[key][g:-g, g:-g])
+            a = act.view(np.float64).ravel()
+            b = ref.view(np.float64).ravel()
+            e = np.abs(a - b).max()/np.abs(b).max()
+            errs[key] = e
+            ok &= e <= rtol
+        if comm.rank == 0:
+            print("%-26s ranks=%d N=%d %s  %s" % (
+                name, comm.size, ntot, "OK  " if ok else "FAIL",
+                " ".join("%s=%.1e" % kv for kv in errs.items())), flush=True)
+        failed += (not ok)
+    comm.barrier()
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    sys.exit(1 if failed else 0)
+
+
+if __name__ == "__main__":
+    main()

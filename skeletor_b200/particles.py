@@ -262,9 +262,10 @@ class Particles:
                 nb_, na_ = nr, nl
             else:
                 nb_, na_ = comm.exchange_counts(nr, nl)
+                # (at least one row per message: no zero-byte NCCL transfers)
                 from_below, from_above = comm.ring_exchange(
-                    self.sbufr[:nr], self.sbufl[:nl],
-                    self.rbufl[:nb_], self.rbufr[:na_])
+                    self.sbufr[:max(nr, 1)], self.sbufl[:max(nl, 1)],
+                    self.rbufl[:max(nb_, 1)], self.rbufr[:max(na_, 1)])
             # keep what belongs here, pass the rest on (pplib2.c:756-866)
             cnt.zero_()
             cnt[0] = nkeep

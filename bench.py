@@ -228,18 +228,23 @@ def b200_arm(a):
     # ---- per-kernel roofline: instrumented pass, CUDA events around each C-ABI call
     peak, peak_src = measured_peak()
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    # (a) the step as it runs by default: push (+ fused boundary epilogue and sort
+    #     histogram) | migration | precounted tile sort | deposit | guards
+    st_ = lambda: torch.cuda.current_stream().cuda_stream
     acc = {"push": [], "migrate": [], "tile_sort": [], "deposit": [], "guards": []}
     for _ in range(3):
         t = [ev() for _ in range(6)]
         torch.cuda.synchronize()
-        t[0].record(); ions._push_kernel(E, B, dt, False)
-        t[1].record(); ions.move()
-        t[2].record(); ions.sort()
+        t[0].record(); ions._push_kernel(E, B, dt, False, count=True)
+        t[1].record()
+        nkeep = ions.move()
+        _lib.call("skb_sort_count_rows", ions._keep.data_ptr(), nkeep, m.c, ions.order,
+                  4, 4, ions._cell_counts.data_ptr(), st_())
+        t[2].record(); ions.sort(precounted=True)
         t[3].record()
         src.t.zero_()
-        ions._ensure_sorted()
         _lib.call("skb_deposit", ions._c, ions.N, src.ptr, m.c, ions.order, 0.0,
-                  ions._tiling_c(), torch.cuda.current_stream().cuda_stream)
+                  ions._tiling_c(), st_())
         t[4].record()
         src.boundaries_set = False
         src.normalize(ions); src.add_guards(); src.copy_guards()
@@ -247,24 +252,77 @@ def b200_arm(a):
         torch.cuda.synchronize()
         for name, i in zip(acc, range(5)):
             acc[name].append(t[i].elapsed_time(t[i + 1]))
+    # (b) alternatives kept in the library, for the record: push without the fused
+    #     histogram + full tile sort (key pass + move); the recompute-twice fused
+    #     push+sort passes
+    acc2 = {"push_plain": [], "tile_sort_full": [], "push_count": [], "push_scatter": []}
+    for _ in range(2):
+        t = [ev() for _ in range(4)]
+        torch.cuda.synchronize()
+        t[0].record(); ions._push_kernel(E, B, dt, False)
+        t[1].record(); ions.move()
+        t[2].record(); ions.sort()
+        t[3].record()
+        torch.cuda.synchronize()
+        acc2["push_plain"].append(t[0].elapsed_time(t[1]))
+        acc2["tile_sort_full"].append(t[2].elapsed_time(t[3]))
+        t = [ev() for _ in range(4)]
+        n_before = ions.N
+        ions.time += dt
+        args, flags = ions._push_args(dt, False)
+        til = ions._tiling_c()
+        epi = ions._epilogue(flags, 0.0)
+        cells = ions._cell_counts.data_ptr()
+        t[0].record()
+        _lib.call("skb_push_count", ions._c, ions.N, E.ptr, B.ptr, *args, til, epi,
+                  4, 4, cells, ions.sbufl.data_ptr(), ions.sbufr.data_ptr(), ions.nbmax,
+                  ions._counts.data_ptr(), comm.rank, comm.size, st_())
+        t[1].record()
+        nl, nr, ovf = ions._counts[:3].tolist()
+        nkeep = ions._exchange(nl, nr)
+        _lib.call("skb_sort_count_rows", ions._keep.data_ptr(), nkeep, args[0], ions.order,
+                  4, 4, cells, st_())
+        _lib.call("skb_sort_scan", cells, args[0], 4, 4, 2048, ions._block_sums.data_ptr(),
+                  ions._tile_offsets.data_ptr(), ions._chunk_first.data_ptr(), st_())
+        out = ions._soa(ions._alt)
+        t[2].record()
+        _lib.call("skb_push_scatter", ions._c, out, ions.N, E.ptr, B.ptr, *args, til, epi,
+                  4, 4, cells, st_())
+        t[3].record()
+        _lib.call("skb_sort_scatter_rows", ions._keep.data_ptr(), nkeep, out, args[0],
+                  ions.order, 4, 4, cells, st_())
+        ions._data, ions._alt = ions._alt, ions._data
+        ions.N = n_before - nl - nr + nkeep
+        ions._n_sorted, ions._sorted = ions.N, True
+        torch.cuda.synchronize()
+        acc2["push_count"].append(t[0].elapsed_time(t[1]))
+        acc2["push_scatter"].append(t[2].elapsed_time(t[3]))
     npart = ions.N
     cells = m.mx*m.myp
     # algorithmic bytes per launch: push 80 B/particle + E,B tiles
-    # 48 B/cell; deposit 40 B/particle + 32 B/cell; sort: 16 B (keys) + 80 B (move)
+    # 48 B/cell; deposit 40 B/particle + 32 B/cell; precounted sort: 80 B (move), full
+    # sort: + 16 B key pass; recompute passes: 40 B read / 40 B read + 40 B written
     alg = {"push": 80.0*npart + 48.0*cells, "deposit": 40.0*npart + 32.0*cells,
-           "tile_sort": 96.0*npart}
-    kern = {}
-    for name, ts in acc.items():
-        tmin = min(ts)
-        kern[name] = {"ms": round(tmin, 4)}
-        if name in alg:
-            gbs = alg[name]/(tmin*1e-3)/1e9
-            kern[name].update({"alg_bytes": alg[name], "achieved_gbs": round(gbs, 1),
-                               "frac": round(gbs/peak, 4)})
+           "tile_sort": 80.0*npart, "push_plain": 80.0*npart + 48.0*cells,
+           "tile_sort_full": 96.0*npart, "push_count": 40.0*npart + 48.0*cells,
+           "push_scatter": 80.0*npart + 48.0*cells}
+
+    def summarize(accd):
+        out = {}
+        for name, ts in accd.items():
+            tmin = min(ts)
+            out[name] = {"ms": round(tmin, 4)}
+            if name in alg:
+                gbs = alg[name]/(tmin*1e-3)/1e9
+                out[name].update({"alg_bytes": alg[name], "achieved_gbs": round(gbs, 1),
+                                  "frac": round(gbs/peak, 4)})
+        return out
+    kern = summarize(acc)
     step_ms = sum(v["ms"] for v in kern.values())
     for v in kern.values():
         v["share"] = round(v["ms"]/step_ms, 4)
-    dom = max(("push", "deposit", "tile_sort"), key=lambda k: kern[k]["ms"])
+    standalone = summarize(acc2)
+    dom = max(("push", "tile_sort", "deposit"), key=lambda k: kern[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": None, "peak_source": peak_src,
@@ -312,7 +370,7 @@ def b200_arm(a):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": workload_config(a, {"particles_per_gpu": n_local}),
-                "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "kernels": kern, "alternative_kernels": standalone, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clk, "impl": "b200"}
         print(json.dumps(line), flush=True)
 

@@ -71,6 +71,8 @@ typedef struct {
 #define SKB_EPI_SHEAR 1      /* shear_periodic_y, particle_boundary.pyx:26-49 */
 #define SKB_EPI_PERIODIC_X 2 /* periodic_x,       particle_boundary.pyx:5-11  */
 #define SKB_EPI_HOLES 4      /* calculate_ihole (unordered list + count)      */
+#define SKB_EPI_COUNT 8      /* histogram of the NEW cell keys of the particles that
+                                stay in the slab (first pass of the tile sort, fused) */
 
 typedef struct {
   int flags;
@@ -78,6 +80,8 @@ typedef struct {
   int *ihole;    /* [ntmax+1]: ihole[0] = count (negated on overflow), then 1-based
                     indices of particles with y < edges[0] or y >= edges[1] */
   int ntmax;
+  int *cell_counts; /* SKB_EPI_COUNT: histogram [ncells+1], cleared by the caller */
+  int key_order, key_tlx, key_tly; /* key definition, as skb_tile_sort */
 } skb_epilogue_t;
 
 int skb_version(void);
@@ -174,6 +178,49 @@ int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long np,
                   const skb_grid_t *grid, int order, int tlx, int tly, int chunk,
                   int *cell_counts, int *block_sums, int *tile_offsets,
                   int *chunk_first_tile, int stable, int *perm, void *stream);
+
+/* ---- fused push + tile sort (B200-native fast path of Particles.push) ----------
+ * Two passes that both recompute the push from the OLD particle state:
+ * skb_push_count:   pass 1 — push in registers; particles that leave the slab are
+ *   packed into sbufl / sbufr exactly as skb_move_pack would (counts[0], counts[1],
+ *   overflow flag counts[2]); all others add to the histogram of their NEW cell key
+ *   (cell_counts is cleared by the call).  The particle arrays are not written.
+ * [caller: exchange buffers; skb_sort_count_rows(arrivals); skb_sort_scan]
+ * skb_push_scatter: pass 2 — push again (bit-identical) and write every staying
+ *   particle to its sorted position in `out`.
+ * [caller: skb_sort_scatter_rows(arrivals)]
+ * epi: SKB_EPI_SHEAR / SKB_EPI_PERIODIC_X flags and S, t (SKB_EPI_HOLES is ignored).
+ * 120 B/particle of HBM traffic instead of 176 B for push + key pass + move. */
+int skb_push_count(skb_particles_t p, long long np, const double *E, const double *B,
+                   const skb_grid_t *grid, int order, double qtmh, double dt,
+                   int modified, double Omega, double S, const skb_tiling_t *tiling,
+                   const skb_epilogue_t *epi, int tlx, int tly, int *cell_counts,
+                   double *sbufl, double *sbufr, int nbmax, int *counts, int rank,
+                   int nvp, void *stream);
+int skb_push_scatter(skb_particles_t p, skb_particles_t out, long long np,
+                     const double *E, const double *B, const skb_grid_t *grid, int order,
+                     double qtmh, double dt, int modified, double Omega, double S,
+                     const skb_tiling_t *tiling, const skb_epilogue_t *epi, int tlx,
+                     int tly, int *cell_pos, void *stream);
+/* pieces of the tile sort, for the fused path: clear the histogram; histogram /
+ * scatter of AoS rows (migration arrivals); scan + tile offsets + chunk table */
+int skb_sort_clear(int *cell_counts, const skb_grid_t *grid, int tlx, int tly,
+                   void *stream);
+int skb_sort_count_rows(const double *rows, int n, const skb_grid_t *grid, int order,
+                        int tlx, int tly, int *cell_counts, void *stream);
+int skb_sort_scan(int *cell_counts, const skb_grid_t *grid, int tlx, int tly, int chunk,
+                  int *block_sums, int *tile_offsets, int *chunk_first_tile,
+                  void *stream);
+int skb_sort_scatter_rows(const double *rows, int n, skb_particles_t out,
+                          const skb_grid_t *grid, int order, int tlx, int tly,
+                          int *cell_pos, void *stream);
+
+/* skb_tile_sort without its histogram pass: cell_counts already holds the histogram
+ * of the keys of in[0..np) (SKB_EPI_COUNT epilogue + skb_sort_count_rows). */
+int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out, long long np,
+                             const skb_grid_t *grid, int order, int tlx, int tly,
+                             int chunk, int *cell_counts, int *block_sums,
+                             int *tile_offsets, int *chunk_first_tile, void *stream);
 
 /* ---- guard cells (NumPy slicing in the reference) ----------------------------
  * nc = doubles per cell (1, 3 or 4).

@@ -34,10 +34,11 @@ class TilingT(C.Structure):
 
 class EpilogueT(C.Structure):
     _fields_ = [("flags", c_int), ("S", c_dbl), ("t", c_dbl), ("ihole", c_vp),
-                ("ntmax", c_int)]
+                ("ntmax", c_int), ("cell_counts", c_vp), ("key_order", c_int),
+                ("key_tlx", c_int), ("key_tly", c_int)]
 
 
-EPI_SHEAR, EPI_PERIODIC_X, EPI_HOLES = 1, 2, 4
+EPI_SHEAR, EPI_PERIODIC_X, EPI_HOLES, EPI_COUNT = 1, 2, 4, 8
 
 _P = ParticlesT
 _G = C.POINTER(GridT)
@@ -63,6 +64,17 @@ SIGNATURES = {
     "skb_cell_keys": [_P, c_ll, _G, c_int, c_int, c_int, c_vp, c_vp],
     "skb_tile_sort": [_P, _P, c_ll, _G, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                       c_vp, c_int, c_vp, c_vp],
+    "skb_push_count": [_P, c_ll, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_int, c_dbl,
+                       c_dbl, _T, _E, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp,
+                       c_int, c_int, c_vp],
+    "skb_push_scatter": [_P, _P, c_ll, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_int,
+                         c_dbl, c_dbl, _T, _E, c_int, c_int, c_vp, c_vp],
+    "skb_sort_clear": [c_vp, _G, c_int, c_int, c_vp],
+    "skb_sort_count_rows": [c_vp, c_int, _G, c_int, c_int, c_int, c_vp, c_vp],
+    "skb_sort_scan": [c_vp, _G, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "skb_sort_scatter_rows": [c_vp, c_int, _P, _G, c_int, c_int, c_int, c_vp, c_vp],
+    "skb_tile_sort_precounted": [_P, _P, c_ll, _G, c_int, c_int, c_int, c_int, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp],
     "skb_copy_guards": [c_vp, c_int, _G, c_vp, c_vp, c_vp],
     "skb_add_guards": [c_vp, c_int, _G, c_int, c_vp, c_vp, c_vp],
     "skb_pack_rows": [c_vp, c_int, _G, c_int, c_int, c_vp, c_vp],
@@ -86,7 +98,8 @@ launches = 0          # number of C-ABI calls made
 kernel_launches = 0   # CUDA kernels those calls launched (bench.py's gpu_launches)
 
 # kernels launched per C-ABI call (memsets are not counted)
-KERNELS_PER_CALL = {"skb_tile_sort": 6, "skb_calculate_ihole": 3, "skb_move_unpack": 3}
+KERNELS_PER_CALL = {"skb_tile_sort": 6, "skb_calculate_ihole": 3, "skb_move_unpack": 3,
+                    "skb_sort_scan": 4, "skb_sort_clear": 0, "skb_tile_sort_precounted": 5}
 
 
 class SkeletorCudaError(RuntimeError):

@@ -150,6 +150,33 @@ __device__ __forceinline__ double wrap_x(double x, double nx) {
   return x;
 }
 
+// ---- sort key (see sort.cu) ----------------------------------------------------
+struct KeyParams {
+  double offx, offy;
+  int order, tlx, tly, ntx, mx, myp;
+};
+
+static inline KeyParams make_keyparams(const DevGrid &g, int order, int tlx, int tly) {
+  KeyParams k;
+  k.offx = g.lbx - 0.5;
+  k.offy = g.lby - 0.5 - g.noff;
+  k.order = order; k.tlx = tlx; k.tly = tly;
+  k.mx = g.mx; k.myp = g.myp;
+  k.ntx = (g.mx + (1 << tlx) - 1) >> tlx;
+  return k;
+}
+
+__device__ __forceinline__ int cell_key(double x, double y, const KeyParams &k) {
+  double xs = x + k.offx, ys = y + k.offy;
+  if (k.order == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+  int ix = (int)xs, iy = (int)ys;
+  ix = min(max(ix, 0), k.mx - 1);
+  iy = min(max(iy, 0), k.myp - 1);
+  const int mxm = (1 << k.tlx) - 1, mym = (1 << k.tly) - 1;
+  return ((((iy >> k.tly) * k.ntx + (ix >> k.tlx)) << (k.tlx + k.tly)) |
+          ((iy & mym) << k.tlx) | (ix & mxm));
+}
+
 #define SKB_CHECK_LAUNCH()                      \
   do {                                          \
     cudaError_t e_ = cudaGetLastError();        \

@@ -33,6 +33,8 @@ struct PushParams {
   int flags, ntmax;
   double vx_boost, x_boost;
   int *ihole;
+  int *cell_counts;   // SKB_EPI_COUNT
+  KeyParams key;
 };
 
 // shear_periodic_y + calculate_ihole + periodic_x for one particle
@@ -89,7 +91,11 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
       stage_window(sB, B, w, wstride, g);
       __syncthreads();
     }
-    for (long long i = s0 + threadIdx.x; i < s1; i += PUSH_THREADS) {
+    // warp-uniform trip count (the fused histogram below is a warp collective)
+    const int lane = threadIdx.x & 31;
+    for (long long base = s0 + (threadIdx.x & ~31); base < s1; base += PUSH_THREADS) {
+      const long long i = base + lane;
+      const bool act = i < s1;
       // pull the lines of the particle this thread handles PF iterations from now
       // into L2: more DRAM requests in flight at no register cost
       const long long ip = i + PUSH_PREFETCH * PUSH_THREADS;
@@ -97,9 +103,113 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
         prefetch_l2(P.x + ip); prefetch_l2(P.y + ip); prefetch_l2(P.vx + ip);
         prefetch_l2(P.vy + ip); prefetch_l2(P.vz + ip);
       }
-      double x = P.x[i], y = P.y[i], vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
-      push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
-      P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
+      int key = -1;
+      if (act) {
+        double x = P.x[i], y = P.y[i], vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
+        push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
+        P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
+        if ((q.flags & SKB_EPI_COUNT) && !(y < g.e0 || y >= g.e1)) key = cell_key(x, y, q.key);
+      }
+      if (q.flags & SKB_EPI_COUNT) {
+        // first pass of the tile sort: one integer atomic per distinct new cell
+        const unsigned peers = __match_any_sync(SKB_FULL, key);
+        if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(q.cell_counts + key, __popc(peers));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Fused push + tile sort in two passes that both RECOMPUTE the push from the old
+// state instead of writing it back in between:
+//   PASS 1 (push_count):   read 40 B, push in registers; leavers are packed straight
+//                          into the exchange buffers (cppmove2's pack, pplib2.c:666-707),
+//                          everybody else adds to the histogram of NEW cell keys.
+//   PASS 2 (push_scatter): read 40 B, push again (bit-identical arithmetic), claim a
+//                          slot in the new cell and write 40 B to the sorted position.
+// 120 B/particle instead of 80 (push) + 16 (key pass) + 80 (move) = 176 B, no hole
+// list and no hole filling.  Arrivals are counted / scattered by the small row kernels
+// of sort.cu between and after the passes.
+struct SortParams {
+  KeyParams key;
+  int *cells;          // PASS 1: histogram; PASS 2: next free slot per cell
+  double *sbufl, *sbufr;
+  int *counts;         // [0] = #sbufl, [1] = #sbufr, [2] = overflow
+  int nbmax, rank, nvp;
+  skb_particles_t out;
+};
+
+template <int ORDER, bool MODIFIED, int PASS>
+__global__ void __launch_bounds__(PUSH_THREADS)
+push_sort_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
+                 const double *__restrict__ B, DevGrid g, DevTiling tl, PushParams q,
+                 SortParams sp, int span, int wstride, int wrows) {
+  extern __shared__ double smem[];
+  double *sE = smem;
+  double *sB = smem + (size_t)wstride * wrows * 3;
+  const int lane = threadIdx.x & 31;
+
+  SegmentIter it;
+  it.init(tl, np, span);
+  long long s0, s1;
+  int tile;
+  while (it.next(tl, s0, s1, tile)) {
+    Window w = tile_window(tile, tl, g);
+    if (tile >= 0) {
+      __syncthreads();
+      stage_window(sE, E, w, wstride, g);
+      stage_window(sB, B, w, wstride, g);
+      __syncthreads();
+    }
+    // warp-uniform trip count: the slot claim below is a warp collective
+    for (long long base = s0 + (threadIdx.x & ~31); base < s1; base += PUSH_THREADS) {
+      const long long i = base + lane;
+      const bool act = i < s1;
+      const long long ip = i + PUSH_PREFETCH * PUSH_THREADS;
+      if (ip < s1) {
+        prefetch_l2(P.x + ip); prefetch_l2(P.y + ip); prefetch_l2(P.vx + ip);
+        prefetch_l2(P.vy + ip); prefetch_l2(P.vz + ip);
+      }
+      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+      int key = -1;
+      if (act) {
+        x = P.x[i]; y = P.y[i]; vx = P.vx[i]; vy = P.vy[i]; vz = P.vz[i];
+        push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
+        if (y < g.e0 || y >= g.e1) {            // leaves the slab
+          if (PASS == 1) {
+            double *buf; int slot;
+            if (y < g.e0) {                      // going down, pplib2.c:674-688
+              if (sp.rank == 0) y += (double)g.ny;
+              slot = atomicAdd(sp.counts + 0, 1); buf = sp.sbufl;
+            } else {                             // going up, pplib2.c:690-705
+              if (sp.rank == sp.nvp - 1) y -= (double)g.ny;
+              slot = atomicAdd(sp.counts + 1, 1); buf = sp.sbufr;
+            }
+            if (slot < sp.nbmax) {
+              double *r = buf + (size_t)slot * 5;
+              r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+            } else {
+              sp.counts[2] = 1;
+            }
+          }
+        } else {
+          key = cell_key(x, y, sp.key);
+        }
+      }
+      const unsigned peers = __match_any_sync(SKB_FULL, key);
+      if (key >= 0) {
+        const int leader = __ffs(peers) - 1;
+        if (PASS == 1) {
+          if (lane == leader) atomicAdd(sp.cells + key, __popc(peers));
+        } else {
+          int slot0 = 0;
+          if (lane == leader) slot0 = atomicAdd(sp.cells + key, __popc(peers));
+          slot0 = __shfl_sync(peers, slot0, leader);
+          const long long d = (long long)slot0 + __popc(peers & ((1u << lane) - 1u));
+          sp.out.x[d] = x; sp.out.y[d] = y; sp.out.vx[d] = vx; sp.out.vy[d] = vy;
+          sp.out.vz[d] = vz;
+        }
+      }
     }
   }
 }
@@ -130,6 +240,8 @@ drift_kernel(skb_particles_t P, long long np, DevGrid g, PushParams q) {
 
 static void fill_epilogue(PushParams &q, const skb_epilogue_t *epi, const DevGrid &g) {
   q.flags = 0; q.ntmax = 0; q.ihole = nullptr; q.vx_boost = 0; q.x_boost = 0;
+  q.cell_counts = nullptr;
+  q.key = make_keyparams(g, 1, 4, 4);
   if (!epi) return;
   q.flags = epi->flags;
   q.ntmax = epi->ntmax;
@@ -137,6 +249,10 @@ static void fill_epilogue(PushParams &q, const skb_epilogue_t *epi, const DevGri
   // particle_boundary.pyx:37-38
   q.vx_boost = epi->S * g.Ly;
   q.x_boost = q.vx_boost * epi->t / g.dx;
+  if (q.flags & SKB_EPI_COUNT) {
+    q.cell_counts = epi->cell_counts;
+    q.key = make_keyparams(g, epi->key_order, epi->key_tlx, epi->key_tly);
+  }
 }
 
 extern "C" int skb_boris_push(skb_particles_t p, long long np, const double *E,
@@ -201,4 +317,76 @@ extern "C" int skb_drift(skb_particles_t p, long long np, double dt,
     SKB_CHECK_LAUNCH();
   }
   return 0;
+}
+
+
+template <int PASS>
+static int launch_push_sort(skb_particles_t p, long long np, const double *E,
+                            const double *B, const DevGrid &g, int order, int modified,
+                            const DevTiling &tl, const PushParams &q, const SortParams &sp,
+                            cudaStream_t st) {
+  if (np <= 0) return 0;
+  const int span = tl.chunk * 2;
+  const int ws = window_stride(tl), wr = window_rows(tl);
+  size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
+  long long nblk = (np + span - 1) / span;
+  void (*k)(skb_particles_t, long long, const double *, const double *, DevGrid, DevTiling,
+            PushParams, SortParams, int, int, int);
+  if (order == 1) k = modified ? push_sort_kernel<1, true, PASS> : push_sort_kernel<1, false, PASS>;
+  else if (order == 2) k = modified ? push_sort_kernel<2, true, PASS> : push_sort_kernel<2, false, PASS>;
+  else return (int)cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<(unsigned)nblk, PUSH_THREADS, smem, st>>>(p, np, E, B, g, tl, q, sp, span, ws, wr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+static PushParams fused_params(const DevGrid &g, double qtmh, double dt, double Omega,
+                               double S, const skb_epilogue_t *epi) {
+  PushParams q;
+  q.k = make_kick(g, qtmh, dt, Omega, S);
+  q.dtdsx = dt / g.dx; q.dtdsy = dt / g.dy;
+  fill_epilogue(q, epi, g);
+  q.flags &= ~(SKB_EPI_HOLES | SKB_EPI_COUNT);   // leavers are packed directly
+  return q;
+}
+
+extern "C" int skb_push_count(skb_particles_t p, long long np, const double *E,
+                              const double *B, const skb_grid_t *grid, int order,
+                              double qtmh, double dt, int modified, double Omega, double S,
+                              const skb_tiling_t *tiling, const skb_epilogue_t *epi,
+                              int tlx, int tly, int *cell_counts, double *sbufl,
+                              double *sbufr, int nbmax, int *counts, int rank, int nvp,
+                              void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGrid g = make_grid(grid);
+  DevTiling tl = make_tiling(tiling);
+  PushParams q = fused_params(g, qtmh, dt, Omega, S, epi);
+  SortParams sp = {};
+  sp.key = make_keyparams(g, order, tlx, tly);
+  sp.cells = cell_counts; sp.sbufl = sbufl; sp.sbufr = sbufr; sp.counts = counts;
+  sp.nbmax = nbmax; sp.rank = rank; sp.nvp = nvp;
+  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = skb_sort_clear(cell_counts, grid, tlx, tly, stream);
+  if (rc) return rc;
+  return launch_push_sort<1>(p, np, E, B, g, order, modified, tl, q, sp, st);
+}
+
+extern "C" int skb_push_scatter(skb_particles_t p, skb_particles_t out, long long np,
+                                const double *E, const double *B, const skb_grid_t *grid,
+                                int order, double qtmh, double dt, int modified,
+                                double Omega, double S, const skb_tiling_t *tiling,
+                                const skb_epilogue_t *epi, int tlx, int tly, int *cell_pos,
+                                void *stream) {
+  DevGrid g = make_grid(grid);
+  DevTiling tl = make_tiling(tiling);
+  PushParams q = fused_params(g, qtmh, dt, Omega, S, epi);
+  SortParams sp = {};
+  sp.key = make_keyparams(g, order, tlx, tly);
+  sp.cells = cell_pos; sp.out = out;
+  return launch_push_sort<2>(p, np, E, B, g, order, modified, tl, q, sp, (cudaStream_t)stream);
 }

@@ -24,32 +24,6 @@
 #define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
-struct KeyParams {
-  double offx, offy;
-  int order, tlx, tly, ntx, mx, myp;
-};
-
-static KeyParams make_keyparams(const DevGrid &g, int order, int tlx, int tly) {
-  KeyParams k;
-  k.offx = g.lbx - 0.5;
-  k.offy = g.lby - 0.5 - g.noff;
-  k.order = order; k.tlx = tlx; k.tly = tly;
-  k.mx = g.mx; k.myp = g.myp;
-  k.ntx = (g.mx + (1 << tlx) - 1) >> tlx;
-  return k;
-}
-
-__device__ __forceinline__ int cell_key(double x, double y, const KeyParams &k) {
-  double xs = x + k.offx, ys = y + k.offy;
-  if (k.order == 2) { xs = xs + 0.5; ys = ys + 0.5; }
-  int ix = (int)xs, iy = (int)ys;
-  ix = min(max(ix, 0), k.mx - 1);
-  iy = min(max(iy, 0), k.myp - 1);
-  const int mxm = (1 << k.tlx) - 1, mym = (1 << k.tly) - 1;
-  return ((((iy >> k.tly) * k.ntx + (ix >> k.tlx)) << (k.tlx + k.tly)) |
-          ((iy & mym) << k.tlx) | (ix & mxm));
-}
-
 __global__ void __launch_bounds__(SORT_THREADS)
 keys_kernel(skb_particles_t P, long long np, KeyParams kp, int *keys) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,8 +154,7 @@ scatter_kernel(skb_particles_t in, skb_particles_t out, long long np, KeyParams 
   }
 }
 
-// after the scatter cell_pos[k] = start of cell k+1; shift back so that on return
-// the array holds the exclusive prefix again (cell starts), entry [ncells] = np
+// chunk c (particles [c*chunk, (c+1)*chunk)) -> tile that holds its first particle
 __global__ void __launch_bounds__(256)
 chunk_table_kernel(const int *__restrict__ tile_offsets, int ntiles, int chunk,
                    int *chunk_first_tile) {
@@ -212,6 +185,90 @@ extern "C" int skb_cell_keys(skb_particles_t p, long long np, const skb_grid_t *
   return 0;
 }
 
+// AoS rows (migration arrivals): histogram / scatter into the sorted SoA arrays
+__global__ void __launch_bounds__(SORT_THREADS)
+count_rows_kernel(const double *__restrict__ rows, int n, KeyParams kp, int *counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicAdd(counts + cell_key(rows[(size_t)i * 5], rows[(size_t)i * 5 + 1], kp), 1);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+scatter_rows_kernel(const double *__restrict__ rows, int n, skb_particles_t out,
+                    KeyParams kp, int *cell_pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double *r = rows + (size_t)i * 5;
+  long long d = atomicAdd(cell_pos + cell_key(r[0], r[1], kp), 1);
+  out.x[d] = r[0]; out.y[d] = r[1]; out.vx[d] = r[2]; out.vy[d] = r[3]; out.vz[d] = r[4];
+}
+
+static int scan_cells(int *cell_counts, const skb_grid_t *grid, int tlx, int tly, int chunk,
+                      int *block_sums, int *tile_offsets, int *chunk_first_tile,
+                      cudaStream_t st) {
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  const int ntiles = ntx * nty;
+  const long long ncells = (long long)ntiles << (tlx + tly);
+  const int n = (int)ncells + 1;  // one extra entry: total
+  const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb > 4096) return (int)cudaErrorInvalidValue;
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums);
+  SKB_CHECK_LAUNCH();
+  scan_top_kernel<<<1, 1024, 0, st>>>(block_sums, nb);
+  SKB_CHECK_LAUNCH();
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums, tlx + tly,
+                                                tile_offsets);
+  SKB_CHECK_LAUNCH();
+  chunk_table_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(tile_offsets, ntiles, chunk,
+                                                           chunk_first_tile);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+static size_t cells_bytes(const skb_grid_t *grid, int tlx, int tly) {
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  return sizeof(int) * ((((size_t)ntx * nty) << (tlx + tly)) + 1);
+}
+
+extern "C" int skb_sort_clear(int *cell_counts, const skb_grid_t *grid, int tlx, int tly,
+                              void *stream) {
+  return (int)cudaMemsetAsync(cell_counts, 0, cells_bytes(grid, tlx, tly),
+                              (cudaStream_t)stream);
+}
+
+extern "C" int skb_sort_scan(int *cell_counts, const skb_grid_t *grid, int tlx, int tly,
+                             int chunk, int *block_sums, int *tile_offsets,
+                             int *chunk_first_tile, void *stream) {
+  return scan_cells(cell_counts, grid, tlx, tly, chunk, block_sums, tile_offsets,
+                    chunk_first_tile, (cudaStream_t)stream);
+}
+
+extern "C" int skb_sort_count_rows(const double *rows, int n, const skb_grid_t *grid,
+                                   int order, int tlx, int tly, int *cell_counts,
+                                   void *stream) {
+  if (n <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  count_rows_kernel<<<(n + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0,
+                      (cudaStream_t)stream>>>(rows, n, kp, cell_counts);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_sort_scatter_rows(const double *rows, int n, skb_particles_t out,
+                                     const skb_grid_t *grid, int order, int tlx, int tly,
+                                     int *cell_pos, void *stream) {
+  if (n <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  scatter_rows_kernel<<<(n + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0,
+                        (cudaStream_t)stream>>>(rows, n, out, kp, cell_pos);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long np,
                              const skb_grid_t *grid, int order, int tlx, int tly,
                              int chunk, int *cell_counts, int *block_sums,
@@ -222,31 +279,36 @@ extern "C" int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long 
   cudaStream_t st = (cudaStream_t)stream;
   DevGrid g = make_grid(grid);
   KeyParams kp = make_keyparams(g, order, tlx, tly);
-  int ntx, nty;
-  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
-  const int ntiles = ntx * nty;
-  const long long ncells = (long long)ntiles << (tlx + tly);
-  const int n = (int)ncells + 1;  // one extra entry: total
-  const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (nb > 4096) return (int)cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(cell_counts, 0, sizeof(int) * (size_t)n, st);
+  cudaError_t e = cudaMemsetAsync(cell_counts, 0, cells_bytes(grid, tlx, tly), st);
   if (e != cudaSuccess) return (int)e;
   const unsigned pblk = (unsigned)((np + SORT_THREADS - 1) / SORT_THREADS);
   if (np > 0) {
     count_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
   }
-  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums);
-  SKB_CHECK_LAUNCH();
-  scan_top_kernel<<<1, 1024, 0, st>>>(block_sums, nb);
-  SKB_CHECK_LAUNCH();
-  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(cell_counts, n, block_sums, tlx + tly,
-                                                tile_offsets);
-  SKB_CHECK_LAUNCH();
+  int rc = scan_cells(cell_counts, grid, tlx, tly, chunk, block_sums, tile_offsets,
+                      chunk_first_tile, st);
+  if (rc) return rc;
   if (np > 0) {
-    chunk_table_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(tile_offsets, ntiles, chunk,
-                                                             chunk_first_tile);
+    scatter_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out,
+                                        long long np, const skb_grid_t *grid, int order,
+                                        int tlx, int tly, int chunk, int *cell_counts,
+                                        int *block_sums, int *tile_offsets,
+                                        int *chunk_first_tile, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  int rc = scan_cells(cell_counts, grid, tlx, tly, chunk, block_sums, tile_offsets,
+                      chunk_first_tile, st);
+  if (rc) return rc;
+  if (np > 0) {
+    const unsigned pblk = (unsigned)((np + SORT_THREADS - 1) / SORT_THREADS);
     scatter_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
   }

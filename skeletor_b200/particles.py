@@ -133,6 +133,8 @@ class Particles:
         self._n_sorted = 0
         self._sorted = False
         self.sort_enabled = True
+        self.fused_push = False   # two-pass recompute path: correct, but the push is
+        # instruction-bound, so it is not faster than push + precounted sort
 
     # -- NumPy-like surface -------------------------------------------------------
     @property
@@ -190,19 +192,30 @@ class Particles:
 
     def _epilogue(self, flags, S=0.0):
         return C.pointer(_lib.EpilogueT(flags, float(S), float(self.time),
-                                        self.ihole.data_ptr(), self.ntmax - 1))
+                                        self.ihole.data_ptr(), self.ntmax - 1,
+                                        self._cell_counts.data_ptr(), self.order,
+                                        TLX, TLY))
 
     # -- tile sort -------------------------------------------------------------------
-    def sort(self):
-        """Counting sort by tile-major stencil-base cell (skb_tile_sort)."""
+    def sort(self, precounted=False):
+        """Counting sort by tile-major stencil-base cell (skb_tile_sort).
+        precounted: the key histogram is already in place (fused into the push
+        epilogue + arrivals), so the 16 B/particle key pass is skipped."""
         if self.N == 0 or not self.sort_enabled:
             self._sorted = False
             return
-        _lib.call("skb_tile_sort", self._c, self._soa(self._alt), self.N,
-                  self.manifold.c, self.order, TLX, TLY, CHUNK,
-                  self._cell_counts.data_ptr(), self._block_sums.data_ptr(),
-                  self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(), 0,
-                  None, _stream())
+        if precounted:
+            _lib.call("skb_tile_sort_precounted", self._c, self._soa(self._alt), self.N,
+                      self.manifold.c, self.order, TLX, TLY, CHUNK,
+                      self._cell_counts.data_ptr(), self._block_sums.data_ptr(),
+                      self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(),
+                      _stream())
+        else:
+            _lib.call("skb_tile_sort", self._c, self._soa(self._alt), self.N,
+                      self.manifold.c, self.order, TLX, TLY, CHUNK,
+                      self._cell_counts.data_ptr(), self._block_sums.data_ptr(),
+                      self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(), 0,
+                      None, _stream())
         self._data, self._alt = self._alt, self._data
         self._n_sorted = self.N
         self._sorted = True
@@ -254,6 +267,28 @@ class Particles:
         nl, nr, ovf = cnt[:3].tolist()
         if ovf:
             raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
+        nkeep = self._exchange(nl, nr)
+        new_n = self.N + nkeep - nh
+        if new_n > self.size:
+            self.info[0] = new_n - self.size
+            raise RuntimeError("particle overflow error, ierr = {}".format(
+                new_n - self.size))
+        _lib.call("skb_move_unpack", self._c, self.N, self.ihole.data_ptr(), nh,
+                  self._keep.data_ptr(), nkeep, self._move_scratch.data_ptr(), st)
+        self.N = new_n
+        self.info[1] = self.info[2] = new_n
+        self._sorted = False
+        return nkeep
+
+    def _exchange(self, nl, nr):
+        """Neighbour exchange of the packed leavers (sbufl: nl rows going down, sbufr:
+        nr rows going up) incl. multi-hop forwarding (pplib2.c:708-866).  Returns the
+        number of arrivals, left as AoS rows in self._keep."""
+        g = self.manifold
+        comm = g.comm
+        gc = g.c
+        st = _stream()
+        cnt = self._counts
         nkeep = 0
         for it in range(2000):
             if comm.size == 1:
@@ -286,16 +321,7 @@ class Particles:
                 more = comm.allreduce(more, op=MAX)
             if more == 0:
                 break
-        new_n = self.N + nkeep - nh
-        if new_n > self.size:
-            self.info[0] = new_n - self.size
-            raise RuntimeError("particle overflow error, ierr = {}".format(
-                new_n - self.size))
-        _lib.call("skb_move_unpack", self._c, self.N, self.ihole.data_ptr(), nh,
-                  self._keep.data_ptr(), nkeep, self._move_scratch.data_ptr(), st)
-        self.N = new_n
-        self.info[1] = self.info[2] = new_n
-        self._sorted = False
+        return nkeep
 
     def periodic_x(self):
         """Applies periodic boundaries on particles along x"""
@@ -319,11 +345,77 @@ class Particles:
         self.periodic_y()
 
     def _push(self, E, B, dt, modified):
-        self._push_kernel(E, B, dt, modified)
-        self.move()
-        self.sort()
+        if self.sort_enabled and self.fused_push and self.N > 0:
+            self._push_fused(E, B, dt, modified)
+        else:
+            count = self.sort_enabled and self.N > 0
+            self._push_kernel(E, B, dt, modified, count=count)
+            nkeep = self.move()
+            if count:
+                # arrivals complete the histogram the push epilogue started
+                _lib.call("skb_sort_count_rows", self._keep.data_ptr(), nkeep,
+                          self.manifold.c, self.order, TLX, TLY,
+                          self._cell_counts.data_ptr(), _stream())
+            self.sort(precounted=count)
 
-    def _push_kernel(self, E, B, dt, modified):
+    def _push_args(self, dt, modified):
+        m = self.manifold
+        qtmh = self.charge/self.mass*dt/2
+        shear = hasattr(m, 'S')
+        flags = _lib.EPI_PERIODIC_X | (_lib.EPI_SHEAR if shear else 0)
+        return (m.c, self.order, float(qtmh), float(dt), int(modified),
+                float(getattr(m, 'Omega', 0.0)) if modified else 0.0,
+                float(getattr(m, 'S', 0.0)) if modified else 0.0), flags
+
+    def _push_fused(self, E, B, dt, modified):
+        """push + boundary epilogue + migration + tile sort as two passes that both
+        recompute the push (skb_push_count / skb_push_scatter): 120 B of HBM traffic
+        per particle instead of 176 B, no hole list, no hole filling."""
+        if self.order not in (1, 2):
+            msg = 'Interpolation order {} not implemented.'
+            raise RuntimeError(msg.format(self.order))
+        m = self.manifold
+        comm = m.comm
+        self.time += dt
+        args, flags = self._push_args(dt, modified)
+        self._ensure_sorted()
+        st = _stream()
+        til = self._tiling_c()
+        epi = self._epilogue(flags, getattr(m, 'S', 0.0))
+        cells = self._cell_counts.data_ptr()
+        cnt = self._counts
+        # pass 1: histogram of new cells; leavers go straight into sbufl / sbufr
+        _lib.call("skb_push_count", self._c, self.N, E.ptr, B.ptr, *args, til, epi,
+                  TLX, TLY, cells, self.sbufl.data_ptr(), self.sbufr.data_ptr(),
+                  self.nbmax, cnt.data_ptr(), comm.rank, comm.size, st)
+        nl, nr, ovf = cnt[:3].tolist()
+        if ovf:
+            raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
+        nkeep = self._exchange(nl, nr)
+        new_n = self.N - nl - nr + nkeep
+        if new_n > self.size:
+            self.info[0] = new_n - self.size
+            raise RuntimeError("particle overflow error, ierr = {}".format(
+                new_n - self.size))
+        gc = args[0]
+        _lib.call("skb_sort_count_rows", self._keep.data_ptr(), nkeep, gc, self.order,
+                  TLX, TLY, cells, st)
+        _lib.call("skb_sort_scan", cells, gc, TLX, TLY, CHUNK,
+                  self._block_sums.data_ptr(), self._tile_offsets.data_ptr(),
+                  self._chunk_first.data_ptr(), st)
+        # pass 2: push again, write every staying particle to its sorted slot
+        out = self._soa(self._alt)
+        _lib.call("skb_push_scatter", self._c, out, self.N, E.ptr, B.ptr, *args, til, epi,
+                  TLX, TLY, cells, st)
+        _lib.call("skb_sort_scatter_rows", self._keep.data_ptr(), nkeep, out, gc,
+                  self.order, TLX, TLY, cells, st)
+        self._data, self._alt = self._alt, self._data
+        self.N = new_n
+        self.info[1] = self.info[2] = new_n
+        self._n_sorted = new_n
+        self._sorted = True
+
+    def _push_kernel(self, E, B, dt, modified, count=False):
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
@@ -336,6 +428,12 @@ class Particles:
         # (particles.py:179-188 in one pass over the particles)
         flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X | (_lib.EPI_SHEAR if shear else 0)
         self._ensure_sorted()
+        if count:
+            # the tiling read by this launch lives in tile_offsets / chunk_first; the
+            # per-cell histogram array is free to be rebuilt for the NEXT ordering
+            flags |= _lib.EPI_COUNT
+            _lib.call("skb_sort_clear", self._cell_counts.data_ptr(), m.c, TLX, TLY,
+                      _stream())
         _lib.call("skb_boris_push", self._c, self.N, E.ptr, B.ptr, m.c, self.order,
                   float(qtmh), float(dt), int(modified),
                   float(getattr(m, 'Omega', 0.0)) if modified else 0.0,

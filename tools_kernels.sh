@@ -5,6 +5,7 @@ import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
         d = json.loads(ln); print('value %.4g  ms/step %.2f' % (d['value'], d['ms_per_step']))
-        for k, v in d['kernels'].items(): print('  %-10s %8.3f ms  frac %s' % (k, v['ms'], v.get('frac')))
+        for grp in ('kernels', 'alternative_kernels'):
+            for k, v in d.get(grp, {}).items(): print('  %-12s %8.3f ms  frac %s' % (k, v['ms'], v.get('frac')))
     else: print(ln.rstrip())
 "

@@ -70,17 +70,21 @@ __device__ __forceinline__ void gather_tsc(const double *sw, const Window &w, in
            wpy * (wmx * v[6][k] + w0x * v[7][k] + wpx * v[8][k]);
 }
 
-// copy the window rows of a Float3 field into shared memory
+// Copy the window rows of a Float3 field into shared memory: one warp per row,
+// lanes along the row (coalesced, no integer division, all loads independent so the
+// whole window is in flight at once).
 __device__ __forceinline__ void stage_window(double *sw, const double *__restrict__ F,
                                              const Window &w, int wstride,
                                              const DevGrid &g) {
   const int wx = (w.x1 - w.x0) * 3, wy = w.y1 - w.y0;
-  for (int idx = threadIdx.x; idx < wx * wy; idx += blockDim.x) {
-    int r = idx / wx, c = idx - r * wx;
-    sw[(size_t)r * wstride * 3 + c] = __ldg(F + ((size_t)(w.y0 + r) * g.mx + w.x0) * 3 + c);
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = wv; r < wy; r += nw) {
+    const double *src = F + ((size_t)(w.y0 + r) * g.mx + w.x0) * 3;
+    double *dst = sw + (size_t)r * wstride * 3;
+#pragma unroll 3
+    for (int c = lane; c < wx; c += 32) dst[c] = __ldg(src + c);
   }
 }
-
 
 struct KickParams {
   double qtmh, dt, Omega, S;

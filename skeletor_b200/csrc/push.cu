@@ -18,6 +18,9 @@
 #include "gather.cuh"
 
 #define PUSH_THREADS 256
+#ifndef PUSH_SPAN_CHUNKS
+#define PUSH_SPAN_CHUNKS 8   // 16384 particles per CTA work item with chunk = 2048
+#endif
 #ifndef PUSH_PREFETCH
 #define PUSH_PREFETCH 1
 #endif
@@ -272,7 +275,9 @@ extern "C" int skb_boris_push(skb_particles_t p, long long np, const double *E,
     if (e != cudaSuccess) return (int)e;
   }
   if (np > 0) {
-    const int span = tl.chunk * 2;  // 4096 particles per CTA with the default chunk
+    int mult = PUSH_SPAN_CHUNKS;   // fewer chunks per CTA when that would idle SMs
+    while (mult > 1 && (np / ((long long)tl.chunk * mult)) < 4 * 148) mult >>= 1;
+    const int span = tl.chunk * mult;
     const int ws = window_stride(tl), wr = window_rows(tl);
     size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
     long long nblk = (np + span - 1) / span;
@@ -326,7 +331,9 @@ static int launch_push_sort(skb_particles_t p, long long np, const double *E,
                             const DevTiling &tl, const PushParams &q, const SortParams &sp,
                             cudaStream_t st) {
   if (np <= 0) return 0;
-  const int span = tl.chunk * 2;
+  int mult = PUSH_SPAN_CHUNKS;
+  while (mult > 1 && (np / ((long long)tl.chunk * mult)) < 4 * 148) mult >>= 1;
+  const int span = tl.chunk * mult;
   const int ws = window_stride(tl), wr = window_rows(tl);
   size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
   long long nblk = (np + span - 1) / span;

@@ -29,6 +29,27 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register is held while the
+// load is in flight
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#define PUSH_THREADS_ 256
+__device__ __forceinline__ void async_load_particle(double *pbuf, int buf, const skb_particles_t &P,
+                                                    long long i) {
+  double *d = pbuf + buf * 5 * PUSH_THREADS_ + threadIdx.x;
+  cp_async8(d, P.x + i);
+  cp_async8(d + PUSH_THREADS_, P.y + i);
+  cp_async8(d + 2 * PUSH_THREADS_, P.vx + i);
+  cp_async8(d + 3 * PUSH_THREADS_, P.vy + i);
+  cp_async8(d + 4 * PUSH_THREADS_, P.vz + i);
+}
+
 struct PushParams {
   KickParams k;
   double dtdsx, dtdsy;
@@ -81,6 +102,7 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
   extern __shared__ double smem[];
   double *sE = smem;
   double *sB = smem + (size_t)wstride * wrows * 3;
+  double *pbuf = sB + (size_t)wstride * wrows * 3;   // [2][5][PUSH_THREADS] particle ring
 
   SegmentIter it;
   it.init(tl, np, span);
@@ -94,21 +116,33 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
       stage_window(sB, B, w, wstride, g);
       __syncthreads();
     }
-    // warp-uniform trip count (the fused histogram below is a warp collective)
+    // Software pipeline through shared memory: the five coordinates of the particle
+    // this thread handles in the NEXT iteration are already on their way
+    // (cp.async, no registers held) while the current one is pushed; the lines of
+    // the iteration after that are being pulled into L2.
+    // Warp-uniform trip count (the fused histogram below is a warp collective).
     const int lane = threadIdx.x & 31;
-    for (long long base = s0 + (threadIdx.x & ~31); base < s1; base += PUSH_THREADS) {
+    const long long first = s0 + (threadIdx.x & ~31);
+    if (first + lane < s1) async_load_particle(pbuf, 0, P, first + lane);
+    cp_async_commit();
+    int buf = 0;
+    for (long long base = first; base < s1; base += PUSH_THREADS, buf ^= 1) {
       const long long i = base + lane;
       const bool act = i < s1;
-      // pull the lines of the particle this thread handles PF iterations from now
-      // into L2: more DRAM requests in flight at no register cost
-      const long long ip = i + PUSH_PREFETCH * PUSH_THREADS;
+      const long long in = i + PUSH_THREADS;
+      if (in < s1) async_load_particle(pbuf, buf ^ 1, P, in);
+      cp_async_commit();
+      const long long ip = i + (PUSH_PREFETCH + 1) * PUSH_THREADS;
       if (ip < s1) {
         prefetch_l2(P.x + ip); prefetch_l2(P.y + ip); prefetch_l2(P.vx + ip);
         prefetch_l2(P.vy + ip); prefetch_l2(P.vz + ip);
       }
+      cp_async_wait_one();   // everything but the group just committed has landed
       int key = -1;
       if (act) {
-        double x = P.x[i], y = P.y[i], vx = P.vx[i], vy = P.vy[i], vz = P.vz[i];
+        const double *pb = pbuf + buf * 5 * PUSH_THREADS + threadIdx.x;
+        double x = pb[0], y = pb[PUSH_THREADS], vx = pb[2 * PUSH_THREADS],
+               vy = pb[3 * PUSH_THREADS], vz = pb[4 * PUSH_THREADS];
         push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
         P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
         if ((q.flags & SKB_EPI_COUNT) && !(y < g.e0 || y >= g.e1)) key = cell_key(x, y, q.key);
@@ -119,6 +153,7 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
         if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(q.cell_counts + key, __popc(peers));
       }
     }
+    cp_async_wait_all();
   }
 }
 
@@ -279,7 +314,7 @@ extern "C" int skb_boris_push(skb_particles_t p, long long np, const double *E,
     while (mult > 1 && (np / ((long long)tl.chunk * mult)) < 4 * 148) mult >>= 1;
     const int span = tl.chunk * mult;
     const int ws = window_stride(tl), wr = window_rows(tl);
-    size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
+    size_t smem = ((size_t)ws * wr * 3 * 2 + 2 * 5 * PUSH_THREADS) * sizeof(double);
     long long nblk = (np + span - 1) / span;
     void (*k)(skb_particles_t, long long, const double *, const double *, DevGrid,
               DevTiling, PushParams, int, int, int);

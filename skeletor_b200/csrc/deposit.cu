@@ -268,11 +268,11 @@ deposit_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
 // Cell-aligned deposit (the fast path when the ordering is exact and cell_end is
 // known): every warp is handed WHOLE cells, so all 32 lanes accumulate the same
 // stencil in registers for the whole cell and there is exactly one warp reduction
-// (butterfly over lanes) and one emit per cell.  Loads are issued UNR iterations
+// (reduce-scatter over lanes) and one emit per cell.  Loads are issued UNR iterations
 // ahead of their use to keep enough bytes in flight with only 16 resident warps.
 // A particle whose stencil base is not the cell it is filed under (caller passed a
 // stale ordering) is deposited on its own through HBM atomics: correct, just slow.
-#define DEP_UNR 4
+template <int ORDER> struct DepUnroll { static constexpr int value = (ORDER == 1) ? 4 : 2; };
 
 template <int NS>
 __device__ __forceinline__ void single_particle_emit(const double (&wx)[NS],
@@ -297,11 +297,56 @@ __device__ __forceinline__ void single_particle_emit(const double (&wx)[NS],
     }
 }
 
+// Warp reduce-scatter of V (power of two <= 32) per-lane values: V-1 + (5 - log2 V)
+// shuffle exchanges instead of 5 V.  On return v[0] of lane l holds the sum over all
+// 32 lanes of value number scatter_index<V>(l); lanes l and l + V hold the same.
+template <int V>
+__device__ __forceinline__ int scatter_index(int lane) {
+  int idx = 0;
+#pragma unroll
+  for (int s = 0, h = V / 2; h >= 1; s++, h >>= 1) idx += ((lane >> s) & 1) * h;
+  return idx;
+}
+
+template <int V>
+__device__ __forceinline__ void warp_reduce_scatter(double *v, int lane) {
+  int bit = 1;
+#pragma unroll
+  for (int h = V / 2; h >= 1; h >>= 1, bit <<= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < h; j++) {
+      const double a = v[j], b = v[j + h];
+      const double send = up ? a : b;
+      const double keep = up ? b : a;
+      v[j] = keep + __shfl_xor_sync(SKB_FULL, send, bit);
+    }
+  }
+#pragma unroll
+  for (; bit < 32; bit <<= 1) v[0] += __shfl_xor_sync(SKB_FULL, v[0], bit);
+}
+
+// add value number idx (= (r*NS + c)*4 + k) of a cell's stencil sums to the window
+template <int NS>
+__device__ __forceinline__ void emit_one(double val, int idx, bool in_window, int ix, int iy,
+                                         double *sw, const Window &w, int wstride,
+                                         double *__restrict__ cur, const DevGrid &g) {
+  const int lo = (NS == 3) ? 1 : 0;
+  const int cell = idx >> 2, k = idx & 3;
+  const int r = cell / NS, c = cell - r * NS;
+  const int x = ix - lo + c, y = iy - lo + r;
+  if (in_window)
+    atomicAdd(sw + ((size_t)(y - w.y0) * wstride + (x - w.x0)) * 4 + k, val);
+  else if (x >= 0 && x < g.mx && y >= 0 && y < g.myp)
+    atomicAdd(cur + ((size_t)y * g.mx + x) * 4 + k, val);
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(DEP_THREADS)
 deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
                      DepParams q, int parts, int wstride, int wrows) {
   constexpr int NS = ORDER + 1;
+  constexpr int UNR = DepUnroll<ORDER>::value;
   extern __shared__ double sw[];
   const int cells_log2 = tl.tlx + tl.tly;
   const int cpp = (1 << cells_log2) / parts;          // cells per CTA
@@ -315,47 +360,67 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
   __syncthreads();
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
-  for (int cell = c0 + wv; cell < c0 + cpp; cell += DEP_THREADS / 32) {
-    const int s = cell ? tl.cell_end[cell - 1] : 0;
-    const int e = tl.cell_end[cell];
-    if (s == e) continue;
-    const int local = cell & ((1 << cells_log2) - 1);
-    Acc<NS> a;
+  // each warp owns a contiguous block of cells (=> a contiguous particle range); the
+  // cell boundaries are fetched 32 at a time, one per lane
+  const int cpw = cpp / (DEP_THREADS / 32);           // cells per warp (>= 1)
+  const int wc0 = c0 + wv * cpw;
+  for (int cb = 0; cb < cpw; cb += 32) {
+    const int mycell = wc0 + cb + lane;
+    const int my_end = (cb + lane < cpw) ? tl.cell_end[mycell] : 0;
+    int prev_end = (wc0 + cb) ? tl.cell_end[wc0 + cb - 1] : 0;
+    const int ncell = min(32, cpw - cb);
+    for (int j = 0; j < ncell; j++) {
+      const int s = prev_end;
+      const int e = __shfl_sync(SKB_FULL, my_end, j);
+      prev_end = e;
+      if (s == e) continue;
+      const int cell = wc0 + cb + j;
+      const int local = cell & ((1 << cells_log2) - 1);
+      Acc<NS> a;
 #pragma unroll
-    for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
-    a.ix = bx + (local & ((1 << tl.tlx) - 1));
-    a.iy = by + (local >> tl.tlx);
-    for (int base = s; base < e; base += 32 * DEP_UNR) {
-      double x[DEP_UNR], y[DEP_UNR], vx[DEP_UNR], vy[DEP_UNR], vz[DEP_UNR];
+      for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+      a.ix = bx + (local & ((1 << tl.tlx) - 1));
+      a.iy = by + (local >> tl.tlx);
+      for (int base = s; base < e; base += 32 * UNR) {
+        double x[UNR], y[UNR], vx[UNR], vy[UNR], vz[UNR];
 #pragma unroll
-      for (int u = 0; u < DEP_UNR; u++) {
-        const int i = base + u * 32 + lane;
-        if (i < e) { x[u] = P.x[i]; y[u] = P.y[i]; vx[u] = P.vx[i]; vy[u] = P.vy[i]; vz[u] = P.vz[i]; }
-      }
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          if (i < e) { x[u] = P.x[i]; y[u] = P.y[i]; vx[u] = P.vx[i]; vy[u] = P.vy[i]; vz[u] = P.vz[i]; }
+        }
 #pragma unroll
-      for (int u = 0; u < DEP_UNR; u++) {
-        const int i = base + u * 32 + lane;
-        if (i < e) {
-          double xs = x[u] + q.offx, ys = y[u] + q.offy;
-          if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
-          int ix, iy;
-          double wx[NS], wy[NS];
-          particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
-          // particle velocity relative to the background shear, deposit.pxd:24
-          const double vxr = vx[u] + q.S * (y[u] * g.dy + g.y0);
-          if (ix == a.ix && iy == a.iy) accumulate<ORDER>(a, wx, wy, vxr, vy[u], vz[u]);
-          else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy[u], vz[u], cur, g);
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          if (i < e) {
+            double xs = x[u] + q.offx, ys = y[u] + q.offy;
+            if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+            int ix, iy;
+            double wx[NS], wy[NS];
+            particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+            // particle velocity relative to the background shear, deposit.pxd:24
+            const double vxr = vx[u] + q.S * (y[u] * g.dy + g.y0);
+            if (ix == a.ix && iy == a.iy) accumulate<ORDER>(a, wx, wy, vxr, vy[u], vz[u]);
+            else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy[u], vz[u], cur, g);
+          }
         }
       }
+      // one reduce-scatter per cell; the NS*NS*4 sums land on as many lanes, which
+      // add them to the window in parallel
+      const int lo = (NS == 3) ? 1 : 0;
+      const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
+                             (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
+      if (NS == 2) {
+        warp_reduce_scatter<16>(a.v, lane);
+        if (lane < 16)
+          emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      } else {
+        warp_reduce_scatter<32>(a.v, lane);
+        warp_reduce_scatter<4>(a.v + 32, lane);
+        emit_one<NS>(a.v[0], scatter_index<32>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        if (lane < 4)
+          emit_one<NS>(a.v[32], 32 + scatter_index<4>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      }
     }
-#pragma unroll
-    for (int i = 0; i < NS * NS * 4; i++) {
-      double t = a.v[i];
-#pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) t += __shfl_down_sync(SKB_FULL, t, d);
-      a.v[i] = t;
-    }
-    if (lane == 0) emit<NS>(a, sw, w, wstride, cur, g);
   }
   __syncthreads();
   flush_window(sw, w, wstride, cur, g);

@@ -33,6 +33,7 @@ def reference_namespace():
         Manifold=Manifold, ShearingManifold=ShearingManifold,
         Particles=sk.Particles, Sources=sk.Sources, Field=sk.Field, Ohm=sk.Ohm,
         Faraday=sk.Faraday, State=sk.State, Float3=sk.Float3, comm=COMM_WORLD,
+        Poisson=sk.Poisson,
         HorowitzStepper=Horowitz, PredictorCorrectorStepper=PC)
     return ns
 

@@ -37,26 +37,31 @@ def main():
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
         Particles=sk.Particles, Sources=sk.Sources, Field=sk.Field, Ohm=sk.Ohm,
         Faraday=sk.Faraday, State=sk.State, Float3=sk.Float3, comm=comm,
+        Poisson=sk.Poisson,
         HorowitzStepper=Horowitz, PredictorCorrectorStepper=PC)
     names = ["ionacoustic_cic", "ionacoustic_tsc", "gyro_cic", "gyro_tsc", "sheared_cic",
-             "sheared_tsc", "predictor_corrector_tsc", "horowitz_cic"]
-    lb = {"ionacoustic_cic": 1}
+             "sheared_tsc", "predictor_corrector_tsc", "horowitz_cic", "poisson"]
+    lb = {"ionacoustic_cic": 1, "poisson": 1}
     failed = 0
     for name in names:
         gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
         with contextlib.redirect_stdout(io.StringIO()):
             res = sc.SCENARIOS[name](ns)
         # gather the slabs on every rank (object allgather: diagnostics path)
-        parts = np.concatenate(comm.allgather(res["particles"]))
-        ntot = comm.allreduce(int(res["N"]))
         g = lb.get(name, 2)
         rtol = 1e-10 if ("horowitz" in name or "predictor" in name) else 1e-12
+        if name == "poisson":
+            rtol = 2e-6       # float32 truncation in the reference (Q3)
         errs = {}
-        ok = ntot == int(gold["N"])
-        e = np.abs(rows(parts) - rows(gold["particles"])).max() / \
-            np.abs(rows(gold["particles"])).max()
-        errs["particles"] = e
-        ok &= e <= rtol
+        ok, ntot = True, 0
+        if "particles" in gold.files:
+            parts = np.concatenate(comm.allgather(res["particles"]))
+            ntot = comm.allreduce(int(res["N"]))
+            ok = ntot == int(gold["N"])
+            e = np.abs(rows(parts) - rows(gold["particles"])).max() / \
+                np.abs(rows(gold["particles"])).max()
+            errs["particles"] = e
+            ok &= e <= rtol
         for key in gold.files:
             if key in ("N", "particles", "time", "t"):
                 continue

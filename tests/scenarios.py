@@ -183,6 +183,22 @@ def ohm_only(sk, seed=15, nx=16, ny=16, lb=1, eta=0.05):
     return dict(E=host(E), B=host(B))
 
 
+def poisson_only(sk, nx=32, ny=64, seed=18):
+    """E = grad del^-2 rho (tests/test_poisson.py): smooth multi-mode charge density"""
+    m = sk.Manifold(nx, ny, sk.comm, lbx=1, lby=1, Lx=1.0, Ly=2.0, ax=0.0, ay=0.0)
+    xg, yg = np.meshgrid(m.x, m.y)
+    rho = sk.Field(m, dtype=np.float64)
+    rho.fill(0.0)
+    rho.active = (np.sin(2*np.pi*xg) * np.cos(2*np.pi*yg/2.0)
+                  + 0.3*np.cos(2*np.pi*3*xg + 0.4) + 0.2*np.sin(2*np.pi*2*yg/2.0))
+    E = sk.Field(m, dtype=sk.Float3)
+    E.fill((0.0, 0.0, 0.0))
+    poisson = sk.Poisson(m)
+    poisson(rho, E)
+    E.copy_guards()
+    return dict(E=host(E))
+
+
 def quiet_lattice(nx, ny, sq, Lx=1.0, Ly=1.0):
     """sq x sq particles per cell on a regular sub-lattice (quiet start)"""
     ax = (np.arange(nx*sq) + 0.5)/(nx*sq)*Lx
@@ -253,6 +269,7 @@ SCENARIOS = {
     "guards_plain": lambda sk: guards_only(sk, shear=False),
     "guards_shear": lambda sk: guards_only(sk, shear=True),
     "ohm_faraday": lambda sk: ohm_only(sk),
+    "poisson": lambda sk: poisson_only(sk),
     "predictor_corrector_tsc": lambda sk: predictor_corrector(sk),
     "horowitz_cic": lambda sk: horowitz(sk),
 }

@@ -26,6 +26,7 @@ def namespace():
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
         Particles=sk.Particles, Sources=sk.Sources, Field=sk.Field, Ohm=sk.Ohm,
         Faraday=sk.Faraday, State=sk.State, Float3=sk.Float3, comm=sk.COMM_SELF,
+        Poisson=sk.Poisson,
         HorowitzStepper=Horowitz, PredictorCorrectorStepper=PC)
 
 
@@ -52,6 +53,10 @@ def test_scenario_matches_reference(name, capsys):
     assert set(res) == set(gold.files)
     # the steppers iterate Ohm/Faraday to convergence and amplify rounding a bit
     rtol = 1e-10 if ("horowitz" in name or "predictor" in name) else 1e-12
+    if name == "poisson":
+        # the reference truncates the spectrum to float32 (operators.pyx:6-8, 97-101;
+        # SURVEY.md Q3): parity is defined at that level
+        rtol = 2e-6
     for key in gold.files:
         if key == "N":
             assert int(res[key]) == int(gold[key])

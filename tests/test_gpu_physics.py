@@ -199,3 +199,67 @@ def test_poisson_solves_gauss_law():
     k2 = kx*kx + ky*ky
     assert np.abs(E['x'].active - (-kx/k2*np.cos(kx*xg + ky*yg))).max() < 5e-8
     assert np.abs(E['y'].active - (-ky/k2*np.cos(kx*xg + ky*yg))).max() < 5e-8
+
+
+def test_landau_damping_of_ion_acoustic_wave():
+    """reference example/landau_ions.py (BASELINE config 2's driver): 32 x 1 grid,
+    2^16 particles per cell, Ti/Te = 1/5, noisy start.  The example only plots; here the
+    decay rate fitted to the maxima of the density amplitude is compared with the
+    kinetic dispersion relation Ti/Te + W(vph/vt) = 0 (example/landau_ions.py:233-242)."""
+    import skeletor_b200 as sk
+    from scipy.optimize import newton
+    from scipy.signal import argrelextrema
+    from scipy.special import wofz
+    nx, ny, npc = 32, 1, 2**16
+    charge = mass = Te = 1.0
+    Ti, A = 1/5, 0.01
+    cs = np.sqrt(Te/mass)
+    N = npc*nx*ny
+    m = sk.Manifold(nx, ny, sk.COMM_SELF)
+    kx = 2*np.pi/m.Lx
+    omega = kx*cs
+    dt = 0.5*m.dx/cs
+    nt = int(2*np.pi*3.0/omega/dt)
+    rng = np.random.default_rng(2024)
+    x = m.Lx*rng.uniform(size=N)
+    y = m.Ly*rng.uniform(size=N)
+    vx = -omega/kx*A*np.sin(kx*x) + np.sqrt(Ti/mass)*rng.normal(size=N)
+    ions = sk.Particles(m, int(1.5*N), charge=charge, mass=mass)
+    ions.initialize(x, y, vx, np.zeros(N), np.zeros(N))
+    assert ions.N == N
+    xg, yg = np.meshgrid(m.x, m.y)
+    S, C = np.sin(kx*xg)/(nx*ny), np.cos(kx*xg)/(nx*ny)
+    E = sk.Field(m, dtype=sk.Float3)
+    E.fill((0.0, 0.0, 0.0))
+    E.copy_guards()
+    B = sk.Field(m, dtype=sk.Float3)
+    B.fill((0.0, 0.0, 0.0))
+    B.copy_guards()
+    sources = sk.Sources(m)
+    ohm = sk.Ohm(m, temperature=Te, charge=charge)
+    sources.deposit(ions, set_boundaries=True)
+    ohm(sources, B, E)
+    E.copy_guards()
+    ampl, time, t = [], [], 0.0
+    for it in range(nt):
+        ions.push(E, B, dt)
+        t += dt
+        sources.deposit(ions, set_boundaries=True)
+        ohm(sources, B, E)
+        E.copy_guards()
+        rho = sources.rho.active
+        ampl.append(np.sqrt((S*rho).sum()**2 + (C*rho).sum()**2))
+        time.append(t)
+    ampl, time = np.array(ampl), np.array(time)
+    peaks = argrelextrema(ampl, np.greater)[0]
+    peaks = peaks[ampl[peaks] > 5e-4]          # above the particle noise floor
+    assert len(peaks) >= 3
+    gamma_fit = np.polyfit(time[peaks[:4]], np.log(ampl[peaks[:4]]), 1)[0]
+
+    def W(z):
+        return 1. + 1j*np.sqrt(0.5*np.pi)*z*wofz(np.sqrt(0.5)*z)
+    vt = np.sqrt(Ti/Te)*cs
+    vph = newton(lambda v: Ti/Te + W(v/vt), cs + 0j)
+    gamma_t = kx*vph.imag
+    assert gamma_t < 0 and gamma_fit < 0
+    assert abs(gamma_fit - gamma_t) < 0.2*abs(gamma_t), (gamma_fit, gamma_t)

@@ -126,7 +126,9 @@ int skb_calculate_ihole(skb_particles_t p, long long np, int *ihole, int ntmax,
  *   edges[0]; y += ny if rank == 0, pplib2.c:676-677) or sbufr (otherwise; y -=
  *   ny if rank == nvp-1, :692-693).  counts[0] = #sbufl, counts[1] = #sbufr
  *   (device ints, zeroed by the call).  A buffer overflow (> nbmax) is reported
- *   as counts[2] = 1 and the surplus is NOT packed.
+ *   as counts[2] = 1 and the surplus is NOT packed.  nh = -(ntmax + 1) means "read
+ *   the hole count from ihole[0] on the device" (no host round trip between push and
+ *   pack); it is echoed into counts[3].
  * skb_move_classify: multi-hop support (pplib2.c:756-866): split a received
  *   buffer into particles that belong here (copied to `keep`, count in
  *   counts[0]) and particles to pass further down / up (appended to sbufl /

@@ -107,25 +107,32 @@ __device__ __forceinline__ void put_row(double *buf, int slot, double x, double 
   r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
 }
 
-// pplib2.c:666-707
+// pplib2.c:666-707.  nh < 0: the hole count is read from ihole[0] on the device (no
+// host round trip between the push and the pack); it is echoed into counts[3].
 __global__ void __launch_bounds__(BT)
-move_pack_kernel(skb_particles_t P, const int *__restrict__ ihole, int nh,
-                 double *sbufl, double *sbufr, int nbmax, int *counts, double e0,
-                 double ny, int rank, int nvp) {
-  int j = blockIdx.x * BT + threadIdx.x;
-  if (j >= nh) return;
-  long long i = (long long)ihole[j + 1] - 1;
-  double y = P.y[i];
-  if (y < e0) {                       // going down
-    if (rank == 0) y += ny;
-    int slot = atomicAdd(counts + 0, 1);
-    if (slot < nbmax) put_row(sbufl, slot, P.x[i], y, P.vx[i], P.vy[i], P.vz[i]);
-    else counts[2] = 1;
-  } else {                            // going up
-    if (rank == nvp - 1) y -= ny;
-    int slot = atomicAdd(counts + 1, 1);
-    if (slot < nbmax) put_row(sbufr, slot, P.x[i], y, P.vx[i], P.vy[i], P.vz[i]);
-    else counts[2] = 1;
+move_pack_kernel(skb_particles_t P, const int *__restrict__ ihole, int nh, double *sbufl,
+                 double *sbufr, int nbmax, int *counts, double e0, double ny, int rank,
+                 int nvp, int ntmax) {
+  if (nh < 0) {
+    nh = ihole[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[3] = nh;
+    if (nh < 0) return;               // overflow / CFL flag: the host raises
+    nh = min(nh, ntmax);
+  }
+  for (int j = blockIdx.x * BT + threadIdx.x; j < nh; j += gridDim.x * BT) {
+    long long i = (long long)ihole[j + 1] - 1;
+    double y = P.y[i];
+    if (y < e0) {                       // going down
+      if (rank == 0) y += ny;
+      int slot = atomicAdd(counts + 0, 1);
+      if (slot < nbmax) put_row(sbufl, slot, P.x[i], y, P.vx[i], P.vy[i], P.vz[i]);
+      else counts[2] = 1;
+    } else {                            // going up
+      if (rank == nvp - 1) y -= ny;
+      int slot = atomicAdd(counts + 1, 1);
+      if (slot < nbmax) put_row(sbufr, slot, P.x[i], y, P.vx[i], P.vy[i], P.vz[i]);
+      else counts[2] = 1;
+    }
   }
 }
 
@@ -261,9 +268,14 @@ extern "C" int skb_move_pack(skb_particles_t p, const int *ihole, int nh, double
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
-  if (nh <= 0) return 0;
-  move_pack_kernel<<<nblk(nh), BT, 0, st>>>(p, ihole, nh, sbufl, sbufr, nbmax, counts,
-                                            grid->edges[0], (double)grid->ny, rank, nvp);
+  if (nh == 0) return 0;
+  // nh < 0: count on the device; -nh - 1 is the capacity of the hole list (ntmax)
+  const int ntmax = (nh < 0) ? -nh - 1 : nh;
+  const unsigned blocks = (nh < 0) ? min(nblk(ntmax), 1184u) : nblk(nh);
+  if (blocks == 0) return 0;
+  move_pack_kernel<<<blocks, BT, 0, st>>>(p, ihole, nh < 0 ? -1 : nh, sbufl, sbufr, nbmax,
+                                          counts, grid->edges[0], (double)grid->ny, rank,
+                                          nvp, ntmax);
   SKB_CHECK_LAUNCH();
   return 0;
 }

@@ -119,6 +119,7 @@ class Particles:
         self.info = np.zeros(7, np.int32)
         # Set initial time
         self.time = time
+        self._N_global = None
         self.N = 0
 
         # tile-sort state
@@ -135,6 +136,29 @@ class Particles:
         self.sort_enabled = True
         self.fused_push = False   # two-pass recompute path: correct, but the push is
         # instruction-bound, so it is not faster than push + precounted sort
+
+    # -- particle counts ------------------------------------------------------------
+    @property
+    def N(self):
+        """number of particles in this slab"""
+        return self._N
+
+    @N.setter
+    def N(self, n):
+        self._N = int(n)
+        self._N_global = None          # unknown until the next reduction
+
+    def _set_N_after_migration(self, n):
+        # migration only moves particles between slabs: the global count is conserved
+        self._N = int(n)
+
+    def N_global(self):
+        """sum of N over all ranks (the reference recomputes it with an allreduce in
+        every normalize, sources.py:55-59; it only changes when N is assigned)"""
+        if self._N_global is None:
+            from .comm import SUM
+            self._N_global = self.manifold.comm.allreduce(int(self._N), op=SUM)
+        return self._N_global
 
     # -- NumPy-like surface -------------------------------------------------------
     @property
@@ -259,12 +283,17 @@ class Particles:
         comm = g.comm
         gc = g.c
         st = _stream()
-        nh = self._ihole_count()
         cnt = self._counts
-        _lib.call("skb_move_pack", self._c, self.ihole.data_ptr(), nh,
+        # the hole count stays on the device for the pack; ONE D2H read afterwards
+        # returns it together with the two buffer counts and the overflow flag
+        _lib.call("skb_move_pack", self._c, self.ihole.data_ptr(), -self.ntmax,
                   self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
                   cnt.data_ptr(), gc, comm.rank, comm.size, st)
-        nl, nr, ovf = cnt[:3].tolist()
+        nl, nr, ovf, nh = cnt[:4].tolist()
+        # Check for ihole overflow error (particles.py:113-117)
+        if nh < 0:
+            msg = "ihole overflow error: ntmax={}, ierr={}"
+            raise RuntimeError(msg.format(self.ihole.numel() - 1, -nh))
         if ovf:
             raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
         nkeep = self._exchange(nl, nr)
@@ -275,7 +304,7 @@ class Particles:
                 new_n - self.size))
         _lib.call("skb_move_unpack", self._c, self.N, self.ihole.data_ptr(), nh,
                   self._keep.data_ptr(), nkeep, self._move_scratch.data_ptr(), st)
-        self.N = new_n
+        self._set_N_after_migration(new_n)
         self.info[1] = self.info[2] = new_n
         self._sorted = False
         return nkeep
@@ -410,7 +439,7 @@ class Particles:
         _lib.call("skb_sort_scatter_rows", self._keep.data_ptr(), nkeep, out, gc,
                   self.order, TLX, TLY, cells, st)
         self._data, self._alt = self._alt, self._data
-        self.N = new_n
+        self._set_N_after_migration(new_n)
         self.info[1] = self.info[2] = new_n
         self._n_sorted = new_n
         self._sorted = True

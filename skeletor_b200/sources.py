@@ -50,8 +50,7 @@ class Sources(Field):
     def normalize(self, particles):
         """Normalize the charge and current densities such that the mean charge
         density is equal to particle.n0 (sources.py:52-63; guards included)."""
-        from .comm import SUM
-        N = self.grid.comm.allreduce(int(particles.N), op=SUM)
+        N = particles.N_global()
         fac = particles.charge*particles.n0*self.grid.nx*self.grid.ny/N
         _lib.call("skb_scale", self.ptr, self.t.numel(), float(fac), _stream())
 

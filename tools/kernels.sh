@@ -1,6 +1,6 @@
 #!/bin/bash
 # prints value, ms/step and per-kernel ms / frac from a short bench run
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>&1 | tail -3 | python -c "
+python $(dirname $0)/../bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>&1 | tail -3 | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):

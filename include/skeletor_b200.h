@@ -158,12 +158,17 @@ int skb_deposit(skb_particles_t p, long long np, double *current,
 /* push_and_deposit_cic/tsc(particles, E, B, qtmh, dt, grid, ihole, current, S,
  *                          update)                   push_and_deposit.pyx:10,91
  * ihole semantics as skb_epilogue_t (unordered list); ihole[0] = -1 flags a
- * particle that moved more than half a cell in the half step (:66-68). */
+ * particle that moved more than half a cell in the half step (:66-68).
+ * next_cell_counts (may be NULL; update only): histogram [ncells+1] of the NEW cell
+ * keys (tiles 2^key_tlx x 2^key_tly) of the particles that stay, cleared by the
+ * caller, for skb_tile_sort_precounted; must not alias tiling->cell_end and needs an
+ * exact ordering (tiling->cell_end, n_sorted == np). */
 int skb_push_and_deposit(skb_particles_t p, long long np, const double *E,
                          const double *B, const skb_grid_t *grid, int order,
                          double qtmh, double dt, int *ihole, int ntmax,
                          double *current, double S, int update,
-                         const skb_tiling_t *tiling, void *stream);
+                         const skb_tiling_t *tiling, int *next_cell_counts,
+                         int key_tlx, int key_tly, void *stream);
 
 /* ---- tile sort (new component; reference's cppdsortp2yl is unused/broken) ----
  * Counting sort of the SoA particle arrays by cell key, out of place.

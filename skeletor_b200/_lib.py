@@ -59,7 +59,7 @@ SIGNATURES = {
     "skb_move_unpack": [_P, c_ll, c_vp, c_int, c_vp, c_int, c_vp, c_vp],
     "skb_deposit": [_P, c_ll, c_vp, _G, c_int, c_dbl, _T, c_vp],
     "skb_push_and_deposit": [_P, c_ll, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_vp,
-                             c_int, c_vp, c_dbl, c_int, _T, c_vp],
+                             c_int, c_vp, c_dbl, c_int, _T, c_vp, c_int, c_int, c_vp],
     "skb_tile_geometry": [_G, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)],
     "skb_cell_keys": [_P, c_ll, _G, c_int, c_int, c_int, c_vp, c_vp],
     "skb_tile_sort": [_P, _P, c_ll, _G, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,

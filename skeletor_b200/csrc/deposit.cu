@@ -426,6 +426,181 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
   flush_window(sw, w, wstride, cur, g);
 }
 
+// ---------------------------------------------------------------------------------
+// Cell-aligned fused push_and_deposit (push_and_deposit.pyx:10-170) for exactly
+// ordered input: as deposit_cells_kernel, plus the E,B windows; every particle is
+// gathered at its OLD position (the one it is filed under), kicked, half-drifted and
+// deposited.  Particles whose half-step stencil base is still their cell (the vast
+// majority at CFL-limited steps) accumulate in registers; the others are deposited on
+// their own (shared-memory window or HBM atomics).  MODE 2 (update): second half
+// drift, x wrap, leaver list, write-back, and the histogram of the new cell keys for
+// the following tile sort (into next_counts, a different array than cell_end).
+template <int NS>
+__device__ __forceinline__ void stray_particle_emit(const double (&wx)[NS],
+                                                    const double (&wy)[NS], int ix, int iy,
+                                                    double vxr, double vy, double vz,
+                                                    double *sw, const Window &w, int wstride,
+                                                    double *__restrict__ cur,
+                                                    const DevGrid &g) {
+  const int lo = (NS == 3) ? 1 : 0;
+  const int x_lo = ix - lo, y_lo = iy - lo;
+  if (x_lo >= w.x0 && x_lo + NS <= w.x1 && y_lo >= w.y0 && y_lo + NS <= w.y1) {
+    double *b = sw + ((size_t)(y_lo - w.y0) * wstride + (x_lo - w.x0)) * 4;
+#pragma unroll
+    for (int r = 0; r < NS; r++)
+#pragma unroll
+      for (int c = 0; c < NS; c++) {
+        const double wgt = wy[r] * wx[c];
+        double *v = b + (r * wstride + c) * 4;
+        atomicAdd(v + 0, wgt);
+        atomicAdd(v + 1, wgt * vxr);
+        atomicAdd(v + 2, wgt * vy);
+        atomicAdd(v + 3, wgt * vz);
+      }
+  } else {
+    single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, cur, g);
+  }
+}
+
+struct PdCellsParams {
+  KeyParams key;
+  int *next_counts;   // MODE 2: histogram of the new keys (may be NULL)
+};
+
+template <int ORDER, int MODE>
+__global__ void __launch_bounds__(DEP_THREADS)
+pd_cells_kernel(skb_particles_t P, const double *__restrict__ E,
+                const double *__restrict__ B, double *__restrict__ cur, DevGrid g,
+                DevTiling tl, DepParams q, FusedParams fq, PdCellsParams pc, int parts,
+                int wstride, int wrows) {
+  constexpr int NS = ORDER + 1;
+  constexpr int UNR = 2;
+  extern __shared__ double smem[];
+  double *sw = smem;
+  double *sE = smem + wstride * wrows * 4;
+  double *sB = sE + wstride * wrows * 3;
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const int pbeg = c0 ? tl.cell_end[c0 - 1] : 0;
+  const int pend = tl.cell_end[c0 + cpp - 1];
+  if (pbeg == pend) return;
+  const Window w = tile_window(tile, tl, g);
+  zero_window(sw, wstride * wrows * 4);
+  stage_window(sE, E, w, wstride, g);
+  stage_window(sB, B, w, wstride, g);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
+  const int cpw = cpp / (DEP_THREADS / 32);
+  const int wc0 = c0 + wv * cpw;
+  for (int cb = 0; cb < cpw; cb += 32) {
+    const int my_end = (cb + lane < cpw) ? tl.cell_end[wc0 + cb + lane] : 0;
+    int prev_end = (wc0 + cb) ? tl.cell_end[wc0 + cb - 1] : 0;
+    const int ncell = min(32, cpw - cb);
+    for (int j = 0; j < ncell; j++) {
+      const int s = prev_end;
+      const int e = __shfl_sync(SKB_FULL, my_end, j);
+      prev_end = e;
+      if (s == e) continue;
+      const int local = (wc0 + cb + j) & ((1 << cells_log2) - 1);
+      Acc<NS> a;
+#pragma unroll
+      for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+      a.ix = bx + (local & ((1 << tl.tlx) - 1));
+      a.iy = by + (local >> tl.tlx);
+      for (int base = s; base < e; base += 32 * UNR) {
+        double x[UNR], y[UNR], vx[UNR], vy[UNR], vz[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          if (i < e) { x[u] = P.x[i]; y[u] = P.y[i]; vx[u] = P.vx[i]; vy[u] = P.vy[i]; vz[u] = P.vz[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          int key = -1;
+          if (i < e) {
+            const double xold = x[u], yold = y[u];
+            fields_and_kick<ORDER, false>(sE, sB, w, wstride, E, B, g, fq.k, x[u], y[u],
+                                          vx[u], vy[u], vz[u]);
+            x[u] = x[u] + vx[u] * fq.d2x;   // first half of the drift
+            y[u] = y[u] + vy[u] * fq.d2y;
+            // more than half a cell in half a step: push_and_deposit.pyx:66-68
+            if (fabs(x[u] - xold) > 0.5 || fabs(y[u] - yold) > 0.5) {
+              if (MODE == 2) atomicOr(fq.ihole, SKB_CFL_BIT);
+              else fq.ihole[0] = -1;
+            }
+            double xs = x[u] + q.offx, ys = y[u] + q.offy;
+            if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+            int ix, iy;
+            double wx[NS], wy[NS];
+            particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+            const double vxr = vx[u] + q.S * (y[u] * g.dy + g.y0);
+            if (ix == a.ix && iy == a.iy) accumulate<ORDER>(a, wx, wy, vxr, vy[u], vz[u]);
+            else stray_particle_emit<NS>(wx, wy, ix, iy, vxr, vy[u], vz[u], sw, w, wstride, cur, g);
+            if (MODE == 2) {
+              x[u] = x[u] + vx[u] * fq.d2x;   // second half of the drift
+              y[u] = y[u] + vy[u] * fq.d2y;
+              x[u] = wrap_x(x[u], (double)g.nx);
+              if (y[u] < g.e0 || y[u] >= g.e1) {      // calculate_ihole_cdef
+                int slot = atomicAdd(fq.ihole, 1) & (SKB_CFL_BIT - 1);
+                if (slot < fq.ntmax) fq.ihole[slot + 1] = i + 1;
+              } else if (pc.next_counts) {
+                key = cell_key(x[u], y[u], pc.key);
+              }
+              P.x[i] = x[u]; P.y[i] = y[u]; P.vx[i] = vx[u]; P.vy[i] = vy[u]; P.vz[i] = vz[u];
+            }
+          }
+          if (MODE == 2 && pc.next_counts) {
+            const unsigned peers = __match_any_sync(SKB_FULL, key);
+            if (key >= 0 && lane == __ffs(peers) - 1)
+              atomicAdd(pc.next_counts + key, __popc(peers));
+          }
+        }
+      }
+      const int lo = (NS == 3) ? 1 : 0;
+      const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
+                             (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
+      if (NS == 2) {
+        warp_reduce_scatter<16>(a.v, lane);
+        if (lane < 16)
+          emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      } else {
+        warp_reduce_scatter<32>(a.v, lane);
+        warp_reduce_scatter<4>(a.v + 32, lane);
+        emit_one<NS>(a.v[0], scatter_index<32>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        if (lane < 4)
+          emit_one<NS>(a.v[32], 32 + scatter_index<4>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      }
+    }
+  }
+  __syncthreads();
+  flush_window(sw, w, wstride, cur, g);
+}
+
+template <int ORDER, int MODE>
+static int launch_pd_cells(skb_particles_t p, const double *E, const double *B,
+                           double *current, const DevGrid &g, const DevTiling &tl,
+                           const DepParams &q, const FusedParams &fq, const PdCellsParams &pc,
+                           cudaStream_t st) {
+  const int ntiles = tl.ntx * tl.nty;
+  const int cells = 1 << (tl.tlx + tl.tly);
+  int parts = 1;
+  while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
+  const int ws = window_stride(tl), wr = window_rows(tl);
+  const size_t smem = (size_t)ws * wr * 10 * sizeof(double);
+  auto k = pd_cells_kernel<ORDER, MODE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<ntiles * parts, DEP_THREADS, smem, st>>>(p, E, B, current, g, tl, q, fq, pc, parts, ws, wr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
 // decode ihole[0] = count | CFL bit into the reference's in-band convention
 __global__ void finalize_fused_ihole_kernel(int *ihole, int ntmax) {
   int v = ihole[0];
@@ -498,7 +673,8 @@ extern "C" int skb_push_and_deposit(skb_particles_t p, long long np, const doubl
                                     const double *B, const skb_grid_t *grid, int order,
                                     double qtmh, double dt, int *ihole, int ntmax,
                                     double *current, double S, int update,
-                                    const skb_tiling_t *tiling, void *stream) {
+                                    const skb_tiling_t *tiling, int *next_cell_counts,
+                                    int key_tlx, int key_tly, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DevGrid g = make_grid(grid);
   DevTiling tl = make_tiling(tiling);
@@ -517,7 +693,23 @@ extern "C" int skb_push_and_deposit(skb_particles_t p, long long np, const doubl
     cudaError_t e = cudaMemsetAsync(ihole, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
   }
-  if (np > 0) {
+  // whole-cells-per-warp path: exact ordering with per-cell ranges covering ALL particles
+  const bool cells_path = tl.tile_offsets && tl.cell_end && tl.n_sorted == np && np > 0 &&
+                          (!next_cell_counts || next_cell_counts != tl.cell_end);
+  if (cells_path) {
+    PdCellsParams pc;
+    pc.key = make_keyparams(g, order, key_tlx, key_tly);
+    pc.next_counts = update ? next_cell_counts : nullptr;
+    int rc;
+    if (order == 1)
+      rc = update ? launch_pd_cells<1, 2>(p, E, B, current, g, tl, q, fq, pc, st)
+                  : launch_pd_cells<1, 1>(p, E, B, current, g, tl, q, fq, pc, st);
+    else
+      rc = update ? launch_pd_cells<2, 2>(p, E, B, current, g, tl, q, fq, pc, st)
+                  : launch_pd_cells<2, 1>(p, E, B, current, g, tl, q, fq, pc, st);
+    if (rc) return rc;
+  } else if (np > 0) {
+    if (next_cell_counts) return (int)cudaErrorInvalidValue;  // histogram needs the cells path
     int rc;
     if (order == 1)
       rc = update ? launch_deposit<1, 2>(p, np, E, B, current, g, tl, q, fq, st)

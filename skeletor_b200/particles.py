@@ -128,6 +128,7 @@ class Particles:
         self._ntx, self._nty = ntx.value, nty.value
         ntiles = self._ntx*self._nty
         self._cell_counts = torch.zeros((ntiles << (TLX + TLY)) + 1, **i32)
+        self._cell_counts_alt = torch.zeros_like(self._cell_counts)
         self._block_sums = torch.zeros(4100, **i32)
         self._tile_offsets = torch.zeros(ntiles + 1, **i32)
         self._chunk_first = torch.zeros(Nmax//CHUNK + 2, **i32)
@@ -493,16 +494,31 @@ class Particles:
         src = self.sources
         src.t.zero_()
         self._ensure_sorted()
+        # histogram of the new cell keys for the tile sort that follows an update, built
+        # by the same kernel into the spare cell array (the live one is being read as
+        # cell_end)
+        count = bool(update) and self.sort_enabled and self._sorted and \
+            self._n_sorted == self.N and self.N > 0
+        nxt = None
+        if count:
+            nxt = self._cell_counts_alt.data_ptr()
+            _lib.call("skb_sort_clear", nxt, self.manifold.c, TLX, TLY, _stream())
         _lib.call("skb_push_and_deposit", self._c, self.N, E.ptr, B.ptr,
                   self.manifold.c, self.order, float(qtmh), float(dt),
                   self.ihole.data_ptr(), self.ntmax - 1, src.ptr, S, int(bool(update)),
-                  self._tiling_c(), _stream())
+                  self._tiling_c(), nxt, TLX, TLY, _stream())
         src.boundaries_set = False
         src.normalize(self)
         src.set_boundaries()
         if update:
-            self.move()
-            self.sort()
+            nkeep = self.move()
+            if count:
+                self._cell_counts, self._cell_counts_alt = \
+                    self._cell_counts_alt, self._cell_counts
+                _lib.call("skb_sort_count_rows", self._keep.data_ptr(), nkeep,
+                          self.manifold.c, self.order, TLX, TLY,
+                          self._cell_counts.data_ptr(), _stream())
+            self.sort(precounted=count)
         elif int(self.ihole[0].item()) < 0:
             self._ihole_count()
 

@@ -211,7 +211,7 @@ def test_push_and_deposit(gk, order, update, sort):
     tE, tB = gu.dev(E), gu.dev(B)
     _lib.call("skb_push_and_deposit", gu.cparts(t), n, tE.data_ptr(),
               tB.data_ptr(), gu.cgrid(g), order, qtmh, dt, ihole.data_ptr(), n,
-              cur.data_ptr(), 0.0, int(update), til, gu.stream())
+              cur.data_ptr(), 0.0, int(update), til, None, 4, 4, gu.stream())
     assert rel(gu.host(cur, orc.Float4), ce) < 1e-12
     assert np.array_equal(gu.sorted_rows(gu.aos(t)), gu.sorted_rows(pe))
     if update:
@@ -233,7 +233,7 @@ def test_push_and_deposit_cfl_flag():
         ihole = torch.zeros(51, dtype=torch.int32, device="cuda")
         _lib.call("skb_push_and_deposit", gu.cparts(t), 100, E.data_ptr(), B.data_ptr(),
                   gu.cgrid(g), 1, 0.0, g.dx, ihole.data_ptr(), 50, cur.data_ptr(), 0.0,
-                  update, None, gu.stream())
+                  update, None, None, 4, 4, gu.stream())
         assert ihole[0].item() == -1
 
 

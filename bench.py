@@ -358,6 +358,16 @@ def b200_arm(a):
                "what": "E,B copied H2D from pinned host memory and sources copied D2H "
                        "inside the timed step; particles stay resident in HBM"}
 
+    # ---- size-independent sanity checks at the full workload size
+    step()
+    n_now = comm.allreduce(int(ions.N), op=sk.comm.SUM) if size > 1 else int(ions.N)
+    rho_sum = float(src.t[m.lby:m.uby, m.lbx:m.ubx, 0].sum().item())
+    if size > 1:
+        rho_sum = comm.allreduce(rho_sum, op=sk.comm.SUM)
+    expect = n_total*ions.charge/a.ppc
+    checks = {"particles_conserved": n_now == n_total,
+              "charge_rel_err": abs(rho_sum - expect)/expect}
+
     cpu = None
     if rank == 0 and size == 1 and not a.no_cpu_baseline:
         from oracle import ref_driver
@@ -371,7 +381,7 @@ def b200_arm(a):
                 "dtype": "f64", "data": "synthetic",
                 "config": workload_config(a, {"particles_per_gpu": n_local}),
                 "roofline": roofline, "kernels": kern, "alternative_kernels": standalone, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clk, "impl": "b200"}
+                "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}
         print(json.dumps(line), flush=True)
 
 

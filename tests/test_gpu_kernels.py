@@ -545,3 +545,109 @@ def test_fused_push_sort_equals_unfused(order, shear):
         parts, N = orc.move(parts, N, [g])
         orc.periodic_x(parts[0][:N[0]], g)
     assert np.array_equal(out[0], gu.sorted_rows(parts[0][:N[0]]))
+
+
+def test_edge_positions_classify_exactly_like_the_reference():
+    """particles sitting exactly on cell faces, slab edges and the periodic seam: the
+    strict / non-strict comparisons and C truncation must match bit for bit"""
+    g = orc.Grid(nx=16, ny=32, rank=1, size=2, lbx=2, lby=2)      # slab rows [16, 32)
+    xs = np.array([0.0, 0.5, 1.0, 7.999999999999999, 8.0, 15.5, 16.0, -0.0, 15.999999999999998])
+    ys = np.array([16.0, 16.5, 17.0, 31.999999999999996, 24.0, 31.5, 16.000000000000004])
+    X, Y = np.meshgrid(xs, ys)
+    n = X.size
+    p = np.zeros(n, orc.Particle)
+    p["x"], p["y"] = X.ravel(), Y.ravel()
+    p["vx"] = np.tile([1.0, -1.0, 0.0], n)[:n]
+    p["vy"] = np.tile([0.0, 1.0, -1.0, 0.5], n)[:n]
+    cg = gu.cgrid(g)
+    for order in (1, 2):
+        exp = g.field(orc.Float4)
+        inside = p[p["x"] < 16.0]          # deposit needs 0 <= x < nx
+        orc.deposit(inside, exp, g, order, 0.0)
+        cur = torch.zeros((g.myp, g.mx, 4), dtype=torch.float64, device="cuda")
+        t = gu.soa(inside)
+        _lib.call("skb_deposit", gu.cparts(t), inside.size, cur.data_ptr(), cg, order, 0.0,
+                  None, gu.stream())
+        assert rel(gu.host(cur, orc.Float4), exp) < 1e-13
+        keys = orc.cell_keys(inside, g, order, (4, 4))
+        kd = torch.zeros(inside.size, dtype=torch.int32, device="cuda")
+        _lib.call("skb_cell_keys", gu.cparts(t), inside.size, cg, order, 4, 4,
+                  kd.data_ptr(), gu.stream())
+        assert np.array_equal(kd.cpu().numpy(), keys)
+    # drift by exactly representable amounts onto / across the edges, then classify
+    exp = p.copy()
+    orc.drift(exp, g, 0.5*g.dx)
+    ih_e = np.zeros(n + 1, np.int32)
+    orc.calculate_ihole(exp, ih_e, g)
+    orc.periodic_x(exp, g)
+    t = gu.soa(p)
+    ihole = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    epi = C.pointer(_lib.EpilogueT(_lib.EPI_HOLES | _lib.EPI_PERIODIC_X, 0.0, 0.0,
+                                   ihole.data_ptr(), n))
+    _lib.call("skb_drift", gu.cparts(t), n, 0.5*g.dx, cg, epi, gu.stream())
+    assert np.array_equal(bits(gu.aos(t)), bits(exp))
+    ih = ihole.cpu().numpy()
+    assert ih[0] == ih_e[0]
+    assert np.array_equal(np.sort(ih[1:ih[0] + 1]), ih_e[1:ih_e[0] + 1])
+
+
+def test_empty_and_full_particle_arrays():
+    """N = 0 everywhere; N == Nmax (no slack); one particle"""
+    import skeletor_b200 as sk
+    m = sk.Manifold(32, 32, sk.COMM_SELF, lbx=2, lby=2)
+    E = sk.Field(m, dtype=sk.Float3)
+    B = sk.Field(m, dtype=sk.Float3)
+    src = sk.Sources(m)
+    ions = sk.Particles(m, 64)
+    assert ions.N == 0
+    ions.push(E, B, 0.01)
+    ions.drift(0.01)
+    src.time = 0.0
+    ions.N = 0
+    # depositing zero particles is a no-op apart from the (division-free) zeroing
+    _lib.call("skb_deposit", ions._c, 0, src.ptr, m.c, 1, 0.0, None, gu.stream())
+    assert float(src.t.abs().sum()) == 0.0
+    # exactly full array, particles streaming through the periodic y boundary
+    n = 64
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    vy = np.where(np.arange(n) % 2 == 0, 3.0, -3.0)
+    with pytest.warns(UserWarning):
+        ions.initialize(x, y, np.zeros(n), vy, np.zeros(n))
+    for it in range(20):
+        ions.push(E, B, 0.01)
+        assert ions.N == n
+    src.deposit(ions, set_boundaries=True)
+    assert np.isclose(src.rho.trim().sum(), 32*32)
+    yy = np.asarray(ions['y'])[:n]
+    assert (yy >= 0).all() and (yy < 32).all()
+
+
+def test_error_behaviour_matches_reference():
+    """in-band errors become the reference's RuntimeErrors (particles.py:113-117)"""
+    import skeletor_b200 as sk
+    m = sk.Manifold(32, 32, sk.COMM_SELF)
+    E = sk.Field(m, dtype=sk.Float3)
+    B = sk.Field(m, dtype=sk.Float3)
+    n = 4000
+    rng = np.random.default_rng(5)
+    ions = sk.Particles(m, 5000, nbmax=8)          # tiny exchange buffers / hole list
+    ions.initialize(rng.uniform(0, 1, n), rng.uniform(0, 1, n), np.zeros(n),
+                    rng.normal(0, 30.0, n), np.zeros(n))
+    with pytest.raises(RuntimeError, match="overflow"):
+        ions.push(E, B, 0.01)
+    # more than half a cell in half a step in push_and_deposit -> ihole[0] = -1
+    ions = sk.Particles(m, 5000)
+    ions.initialize(rng.uniform(0, 1, n), rng.uniform(0, 1, n), np.full(n, 100.0),
+                    np.zeros(n), np.zeros(n))
+    B.copy_guards()
+    E.copy_guards()
+    with pytest.raises(RuntimeError, match="ihole overflow error"):
+        ions.push_and_deposit(E, B, 0.01, True)
+    # interpolation order / guard layer checks
+    with pytest.raises(AssertionError):
+        sk.Particles(m, 10, order=2)               # TSC needs lbx >= 2
+    f = sk.Field(m, dtype=sk.Float3)
+    f.copy_guards()
+    with pytest.raises(AssertionError):
+        f.copy_guards()                            # field.py:106

@@ -133,7 +133,9 @@ int skb_calculate_ihole(skb_particles_t p, long long np, int *ihole, int ntmax,
  *   buffer into particles that belong here (copied to `keep`, count in
  *   counts[0]) and particles to pass further down / up (appended to sbufl /
  *   sbufr with the edge-rank y wrap; counts[1], counts[2]; counts[3] = overflow).
- *   The caller zeroes counts[0..3].
+ *   The caller zeroes counts[0..3].  nrecv = -(capacity + 1): header mode for the
+ *   peer-memory exchange — the row count is the first double of rbuf and the rows
+ *   follow a 5-double header.
  * skb_move_unpack: put `nin` incoming particles (AoS rows in `in`) into the
  *   holes listed in ihole[1..nh], append what is left at np, or — if holes remain
  *   — compact the tail into them (pplib2.c:883-952).  New count = np + nin - nh

@@ -54,6 +54,9 @@ class SelfComm:
     def exchange_counts(self, n_up, n_down):
         return n_up, n_down
 
+    def halo_exchange(self, up, down):
+        return up, down
+
 
 class TorchComm:
     """torch.distributed-backed communicator (one process per GPU)."""
@@ -65,6 +68,7 @@ class TorchComm:
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+        self._halo_arena = None
 
     def Get_rank(self):
         return self.rank
@@ -154,6 +158,19 @@ class TorchComm:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         return from_below, from_above
+
+    def halo_exchange(self, up, down):
+        """ring exchange of two equally-shaped halo messages; through NVLink peer
+        memory (skeletor_b200/peer.py) when available, else NCCL send/recv"""
+        from . import peer
+        if not (up.is_cuda and peer.available(self)):
+            return self.ring_exchange(up, down)
+        n = max(up.numel(), down.numel())
+        if self._halo_arena is None or self._halo_arena.cap < n:
+            # (collective: every rank reaches the same exchange with the same sizes)
+            self._halo_arena = peer.PeerArena(self, max(n, 1 << 16))
+        fb, fa = self._halo_arena.exchange(up, down)
+        return fb[:up.numel()].view(up.shape), fa[:down.numel()].view(down.shape)
 
     def exchange_counts(self, n_up, n_down):
         """tell the neighbours how many particles are coming; returns

@@ -136,28 +136,34 @@ move_pack_kernel(skb_particles_t P, const int *__restrict__ ihole, int nh, doubl
   }
 }
 
-// pplib2.c:756-866: particles that arrived but do not belong here are passed on
+// pplib2.c:756-866: particles that arrived but do not belong here are passed on.
+// nrecv < 0: header mode (peer-memory exchange) — the count is the first double of
+// rbuf, the rows follow the 5-double header; -nrecv - 1 is the row capacity.
 __global__ void __launch_bounds__(BT)
 move_classify_kernel(const double *__restrict__ rbuf, int nrecv, double *keep,
                      double *sbufl, double *sbufr, int nbmax, int *counts, double e0,
                      double e1, double ny, int rank, int nvp) {
-  int j = blockIdx.x * BT + threadIdx.x;
-  if (j >= nrecv) return;
-  const double *r = rbuf + (size_t)j * 5;
-  double y = r[1];
-  if (y < e0) {
-    if (rank == 0) y += ny;
-    int slot = atomicAdd(counts + 1, 1);
-    if (slot < nbmax) put_row(sbufl, slot, r[0], y, r[2], r[3], r[4]);
-    else counts[3] = 1;
-  } else if (y >= e1) {
-    if (rank == nvp - 1) y -= ny;
-    int slot = atomicAdd(counts + 2, 1);
-    if (slot < nbmax) put_row(sbufr, slot, r[0], y, r[2], r[3], r[4]);
-    else counts[3] = 1;
-  } else {
-    int slot = atomicAdd(counts + 0, 1);
-    put_row(keep, slot, r[0], y, r[2], r[3], r[4]);
+  if (nrecv < 0) {
+    nrecv = min((int)rbuf[0], -nrecv - 1);
+    rbuf += 5;
+  }
+  for (int j = blockIdx.x * BT + threadIdx.x; j < nrecv; j += gridDim.x * BT) {
+    const double *r = rbuf + (size_t)j * 5;
+    double y = r[1];
+    if (y < e0) {
+      if (rank == 0) y += ny;
+      int slot = atomicAdd(counts + 1, 1);
+      if (slot < nbmax) put_row(sbufl, slot, r[0], y, r[2], r[3], r[4]);
+      else counts[3] = 1;
+    } else if (y >= e1) {
+      if (rank == nvp - 1) y -= ny;
+      int slot = atomicAdd(counts + 2, 1);
+      if (slot < nbmax) put_row(sbufr, slot, r[0], y, r[2], r[3], r[4]);
+      else counts[3] = 1;
+    } else {
+      int slot = atomicAdd(counts + 0, 1);
+      put_row(keep, slot, r[0], y, r[2], r[3], r[4]);
+    }
   }
 }
 
@@ -283,8 +289,10 @@ extern "C" int skb_move_pack(skb_particles_t p, const int *ihole, int nh, double
 extern "C" int skb_move_classify(const double *rbuf, int nrecv, double *keep,
                                  double *sbufl, double *sbufr, int nbmax, int *counts,
                                  const skb_grid_t *grid, int rank, int nvp, void *stream) {
-  if (nrecv <= 0) return 0;
-  move_classify_kernel<<<nblk(nrecv), BT, 0, (cudaStream_t)stream>>>(
+  if (nrecv == 0) return 0;
+  const unsigned blocks = (nrecv < 0) ? min(nblk(-nrecv - 1), 592u) : nblk(nrecv);
+  if (blocks == 0) return 0;
+  move_classify_kernel<<<blocks, BT, 0, (cudaStream_t)stream>>>(
       rbuf, nrecv, keep, sbufl, sbufr, nbmax, counts, grid->edges[0], grid->edges[1],
       (double)grid->ny, rank, nvp);
   SKB_CHECK_LAUNCH();

@@ -160,7 +160,7 @@ class Field(DeviceArray):
     def _halo_exchange(self, up_rows, down_rows):
         """send `up_rows` to the rank above and `down_rows` to the rank below;
         returns (from_below, from_above).  Replaces send_up/send_dn (field.py:52-58)"""
-        return self.grid.comm.ring_exchange(up_rows, down_rows)
+        return self.grid.comm.halo_exchange(up_rows, down_rows)
 
     def _pack_rows(self, iy0, nrows):
         g = self.grid

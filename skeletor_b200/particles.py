@@ -102,9 +102,16 @@ class Particles:
 
         # Location of hole left in particle arrays (particles.py:40)
         self.ihole = torch.zeros(ntmax, **i32)
-        # Buffer arrays for the neighbour exchange (AoS rows of 5 doubles)
-        self.sbufl = torch.zeros((nbmax, 5), **f64)
-        self.sbufr = torch.zeros((nbmax, 5), **f64)
+        # Buffer arrays for the neighbour exchange (AoS rows of 5 doubles); one
+        # header row in front of each send buffer carries the row count when the
+        # exchange goes through NVLink peer memory (skeletor_b200/peer.py)
+        self._sbl = torch.zeros((nbmax + 1, 5), **f64)
+        self._sbr = torch.zeros((nbmax + 1, 5), **f64)
+        self.sbufl = self._sbl[1:]
+        self.sbufr = self._sbr[1:]
+        from . import peer
+        self._mig = peer.PeerArena(manifold.comm, (nbmax + 1)*5) \
+            if peer.available(manifold.comm) else None
         self.rbufl = torch.zeros((nbmax, 5), **f64)
         self.rbufr = torch.zeros((nbmax, 5), **f64)
         self._keep = torch.zeros((2*nbmax, 5), **f64)
@@ -320,6 +327,8 @@ class Particles:
         st = _stream()
         cnt = self._counts
         nkeep = 0
+        if self._mig is not None:
+            return self._exchange_peer(nl, nr)
         for it in range(2000):
             if comm.size == 1:
                 # nvp == 1: rbufl = sbufr, rbufr = sbufl (pplib2.c:715-730)
@@ -350,6 +359,38 @@ class Particles:
                 from .comm import MAX
                 more = comm.allreduce(more, op=MAX)
             if more == 0:
+                break
+        return nkeep
+
+    def _exchange_peer(self, nl, nr):
+        """_exchange through NVLink peer memory: header + rows are copied straight into
+        the neighbours' slots, one device-side barrier, classification with device-side
+        counts, and the "does anybody still forward?" agreement (cppimax, pplib2.c:873)
+        through per-rank flag words — no NCCL call and ONE host sync per round."""
+        g = self.manifold
+        comm = g.comm
+        gc = g.c
+        st = _stream()
+        cnt = self._counts
+        arena = self._mig
+        nkeep = 0
+        for it in range(2000):
+            self._sbl[0, :1].fill_(float(nl))
+            self._sbr[0, :1].fill_(float(nr))
+            from_below, from_above = arena.exchange(self._sbr[:nr + 1], self._sbl[:nl + 1])
+            cnt.zero_()
+            cnt[:1].fill_(nkeep)
+            for buf in (from_below, from_above):
+                _lib.call("skb_move_classify", buf.data_ptr(), -(self.nbmax + 1),
+                          self._keep.data_ptr(), self.sbufl.data_ptr(),
+                          self.sbufr.data_ptr(), self.nbmax, cnt.data_ptr(), gc,
+                          comm.rank, comm.size, st)
+            flags = arena.all_flags((cnt[1] + cnt[2]) > 0)
+            vals = torch.cat([cnt[:4].to(torch.float64), flags]).tolist()
+            nkeep, nl, nr, ovf = (int(v) for v in vals[:4])
+            if ovf or nkeep > self._keep.shape[0]:
+                raise RuntimeError("particle buffer overflow while forwarding")
+            if not any(vals[4:]):
                 break
         return nkeep
 

@@ -1,0 +1,88 @@
+"""Neighbour exchange through NVLink peer memory instead of NCCL point-to-point.
+
+Every rank owns a slice of symmetric memory (torch.distributed._symmetric_memory:
+one CUDA allocation per rank, mapped into every peer over NVLink/NVSwitch).  A ring
+exchange is then: two device-to-device copies straight into the neighbours' slots
+(`up` into the rank above's from-below slot, `down` into the rank below's from-above
+slot) followed by one device-side barrier, all stream-ordered — no NCCL call, no host
+synchronisation, ~15 us instead of ~150 us per exchange.  Halo rows (field.py:52-58 in
+the reference) and migrating particles (pplib2.c:741-753) both go through it.
+
+Slots are double-buffered by exchange parity: a rank can run at most one barrier ahead
+of its neighbours, so exchange k+1 (other parity) never overwrites data a slower rank
+is still reading from exchange k.
+"""
+import os
+
+import torch
+
+
+def available(comm):
+    """peer path usable: NCCL world on CUDA, symmetric memory importable, not disabled"""
+    if os.environ.get("SKELETOR_B200_PEER", "1") == "0":
+        return False
+    if getattr(comm, "size", 1) <= 1 or getattr(comm, "backend", None) != "nccl":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+    except Exception:
+        return False
+    return torch.cuda.is_available()
+
+
+class PeerArena:
+    """2 (parity) x 2 (from_below, from_above) slots of `slot_doubles` float64 each,
+    plus 2 x size flag words, in symmetric memory."""
+
+    def __init__(self, comm, slot_doubles):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.comm = comm
+        self.cap = int(slot_doubles)
+        self.size, self.rank = comm.size, comm.rank
+        self.nflag = 2*self.size
+        n = 4*self.cap + self.nflag
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.t = symm.empty((n,), dtype=torch.float64, device=dev)
+        group = comm.group if comm.group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.t, group.group_name)
+        self.t.zero_()
+        above = (self.rank + 1) % self.size
+        below = (self.rank - 1) % self.size
+        self.above_buf = self.hdl.get_buffer(above, (n,), torch.float64)
+        self.below_buf = self.hdl.get_buffer(below, (n,), torch.float64)
+        self.all_bufs = [self.hdl.get_buffer(r, (n,), torch.float64)
+                         for r in range(self.size)]
+        self.k = 0
+        self.hdl.barrier()
+
+    def _slot(self, parity, which):
+        return (parity*2 + which)*self.cap
+
+    def exchange(self, up, down):
+        """`up` -> rank above, `down` -> rank below (flattened float64 tensors, at most
+        `cap` elements).  Returns (from_below, from_above): views of this rank's own
+        slots (full capacity), valid until the exchange after the next one."""
+        p = self.k & 1
+        self.k += 1
+        u, d = up.reshape(-1), down.reshape(-1)
+        o = self._slot(p, 0)
+        self.above_buf[o:o + u.numel()].copy_(u)
+        o = self._slot(p, 1)
+        self.below_buf[o:o + d.numel()].copy_(d)
+        self.hdl.barrier()
+        o0, o1 = self._slot(p, 0), self._slot(p, 1)
+        return self.t[o0:o0 + self.cap], self.t[o1:o1 + self.cap]
+
+    def all_flags(self, flag):
+        """every rank publishes one float64 device scalar to all ranks; returns the
+        local view [size] of everybody's value after a barrier (no host sync)"""
+        p = self.k & 1
+        self.k += 1
+        o = 4*self.cap + p*self.size + self.rank
+        f = flag.reshape(1).to(torch.float64)
+        for buf in self.all_bufs:
+            buf[o:o + 1].copy_(f)
+        self.hdl.barrier()
+        o = 4*self.cap + p*self.size
+        return self.t[o:o + self.size]

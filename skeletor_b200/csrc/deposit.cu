@@ -409,7 +409,7 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
       const int lo = (NS == 3) ? 1 : 0;
       const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
                              (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
-      if (NS == 2) {
+      if constexpr (NS == 2) {
         warp_reduce_scatter<16>(a.v, lane);
         if (lane < 16)
           emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
@@ -563,7 +563,7 @@ pd_cells_kernel(skb_particles_t P, const double *__restrict__ E,
       const int lo = (NS == 3) ? 1 : 0;
       const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
                              (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
-      if (NS == 2) {
+      if constexpr (NS == 2) {
         warp_reduce_scatter<16>(a.v, lane);
         if (lane < 16)
           emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);

@@ -133,24 +133,39 @@ scan_apply_kernel(int *a, int n, const int *__restrict__ block_sums, int cells_l
 }
 
 // scatter: cell_pos[key] holds the next free slot of the cell (starts at the
-// exclusive prefix); a warp claims a block of slots per distinct key.
+// exclusive prefix); a warp claims a block of slots per distinct key.  Each thread
+// moves SCATTER_ITEMS particles (warp-strided), with all their loads issued before
+// the first dependent atomic: more bytes in flight per warp.
+#ifndef SCATTER_ITEMS
+#define SCATTER_ITEMS 2
+#endif
 __global__ void __launch_bounds__(SORT_THREADS)
 scatter_kernel(skb_particles_t in, skb_particles_t out, long long np, KeyParams kp,
                int *cell_pos) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool act = i < np;
-  double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
-  if (act) { x = in.x[i]; y = in.y[i]; vx = in.vx[i]; vy = in.vy[i]; vz = in.vz[i]; }
-  int key = act ? cell_key(x, y, kp) : -1;
-  unsigned peers = __match_any_sync(SKB_FULL, key);
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (act && lane == leader) base = atomicAdd(cell_pos + key, __popc(peers));
-  base = __shfl_sync(SKB_FULL, base, leader);
-  if (act) {
-    long long d = (long long)base + __popc(peers & ((1u << lane) - 1u));
-    out.x[d] = x; out.y[d] = y; out.vx[d] = vx; out.vy[d] = vy; out.vz[d] = vz;
+  const long long warp0 = ((long long)blockIdx.x * SORT_THREADS + (threadIdx.x & ~31)) *
+                          SCATTER_ITEMS;
+  double x[SCATTER_ITEMS], y[SCATTER_ITEMS], vx[SCATTER_ITEMS], vy[SCATTER_ITEMS],
+      vz[SCATTER_ITEMS];
+#pragma unroll
+  for (int u = 0; u < SCATTER_ITEMS; u++) {
+    const long long i = warp0 + u * 32 + lane;
+    if (i < np) { x[u] = in.x[i]; y[u] = in.y[i]; vx[u] = in.vx[i]; vy[u] = in.vy[i]; vz[u] = in.vz[i]; }
+  }
+#pragma unroll
+  for (int u = 0; u < SCATTER_ITEMS; u++) {
+    const long long i = warp0 + u * 32 + lane;
+    const bool act = i < np;
+    int key = act ? cell_key(x[u], y[u], kp) : -1;
+    unsigned peers = __match_any_sync(SKB_FULL, key);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (act && lane == leader) base = atomicAdd(cell_pos + key, __popc(peers));
+    base = __shfl_sync(SKB_FULL, base, leader);
+    if (act) {
+      long long d = (long long)base + __popc(peers & ((1u << lane) - 1u));
+      out.x[d] = x[u]; out.y[d] = y[u]; out.vx[d] = vx[u]; out.vy[d] = vy[u]; out.vz[d] = vz[u];
+    }
   }
 }
 
@@ -290,7 +305,9 @@ extern "C" int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long 
                       chunk_first_tile, st);
   if (rc) return rc;
   if (np > 0) {
-    scatter_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
+    const unsigned sblk = (unsigned)((np + SORT_THREADS * SCATTER_ITEMS - 1) /
+                                     (SORT_THREADS * SCATTER_ITEMS));
+    scatter_kernel<<<sblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
   }
   return 0;
@@ -308,8 +325,9 @@ extern "C" int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out,
                       chunk_first_tile, st);
   if (rc) return rc;
   if (np > 0) {
-    const unsigned pblk = (unsigned)((np + SORT_THREADS - 1) / SORT_THREADS);
-    scatter_kernel<<<pblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
+    const unsigned sblk = (unsigned)((np + SORT_THREADS * SCATTER_ITEMS - 1) /
+                                     (SORT_THREADS * SCATTER_ITEMS));
+    scatter_kernel<<<sblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
   }
   return 0;

@@ -18,16 +18,31 @@ import torch
 
 
 def available(comm):
-    """peer path usable: NCCL world on CUDA, symmetric memory importable, not disabled"""
+    """Peer path usable?  NCCL world on CUDA, not disabled (SKELETOR_B200_PEER=0), and a
+    one-time probe (allocate + rendezvous + barrier + peer copy) succeeded on EVERY rank
+    — the ranks agree on the outcome through an allreduce, so they never diverge between
+    the peer path and the NCCL fallback."""
     if os.environ.get("SKELETOR_B200_PEER", "1") == "0":
         return False
     if getattr(comm, "size", 1) <= 1 or getattr(comm, "backend", None) != "nccl":
         return False
-    try:
-        import torch.distributed._symmetric_memory  # noqa: F401
-    except Exception:
-        return False
-    return torch.cuda.is_available()
+    ok = getattr(comm, "_peer_ok", None)
+    if ok is None:
+        good = 1
+        try:
+            a = PeerArena(comm, 64)
+            src = torch.full((8,), float(comm.rank), dtype=torch.float64, device=a.t.device)
+            fb, fa = a.exchange(src, src)
+            torch.cuda.synchronize()
+            below, above = (comm.rank - 1) % comm.size, (comm.rank + 1) % comm.size
+            if float(fb[0]) != float(below) or float(fa[0]) != float(above):
+                good = 0
+        except Exception:
+            good = 0
+        from .comm import MIN
+        ok = bool(comm.allreduce(good, op=MIN))
+        comm._peer_ok = ok
+    return ok
 
 
 class PeerArena:

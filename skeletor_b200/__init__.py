@@ -14,7 +14,8 @@ from .ohm import Ohm
 from .faraday import Faraday
 from .poisson import Poisson
 from .state import State
-from .initial_condition import InitialCondition
+from .initial_condition import InitialCondition, DensityPertubation
+from .io import IO
 from .manifolds.second_order import Manifold, ShearingManifold
 from . import comm
 from .comm import COMM_WORLD, COMM_SELF

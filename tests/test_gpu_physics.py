@@ -263,3 +263,50 @@ def test_landau_damping_of_ion_acoustic_wave():
     gamma_t = kx*vph.imag
     assert gamma_t < 0 and gamma_fit < 0
     assert abs(gamma_fit - gamma_t) < 0.2*abs(gamma_t), (gamma_fit, gamma_t)
+
+
+def test_density_perturbation_quiet_start():
+    """reference tests/test_density_perturbation.py (quiet start, :79): the y-averaged
+    deposited density of the displaced lattice matches 1 + ampl cos(kx x)"""
+    import skeletor_b200 as sk
+    nx, ny, npc, ampl = 128, 8, 256, 0.1
+    Lx, Ly = 4, 1
+    m = sk.Manifold(nx, ny, sk.COMM_SELF, Lx=Lx, Ly=Ly, x0=-Lx/2, y0=-Ly/2)
+    N = npc*nx*ny
+    ions = sk.Particles(m, int(1.5*N), charge=1.0, mass=1.0)
+    sk.DensityPertubation(npc, 1, 0, ampl, quiet=True, global_init=True)(m, ions)
+    src = sk.Sources(m)
+    src.deposit(ions)
+    assert np.isclose(src.rho.sum(), ions.N*1.0/npc)
+    src.add_guards()
+    src.copy_guards()
+    assert np.isclose(src.rho.trim().sum(), N*1.0/npc)
+    rho = src.rho.trim().mean(axis=0)
+    rho_exact = 1 + ampl*np.cos(2*np.pi/Lx*m.x)
+    assert np.sqrt(np.mean((rho - rho_exact)**2)) < 0.005*ampl
+
+
+def test_io_snapshots(tmp_path, monkeypatch):
+    """reference skeletor/io.py: run directory, info.p, fields.NNNN.npz, log"""
+    import pickle
+    import skeletor_b200 as sk
+    monkeypatch.chdir(tmp_path)
+    m = sk.Manifold(16, 8, sk.COMM_SELF)
+    src = sk.Sources(m)
+    E = sk.Field(m, dtype=sk.Float3)
+    rng = np.random.default_rng(0)
+    src['t'][...] = rng.uniform(0, 1, (m.myp, m.mx))
+    E['x'][...] = rng.uniform(0, 1, (m.myp, m.mx))
+    nx, dt = 16, 0.5
+    io = sk.IO(str(tmp_path/"run"), locals(), __file__, tag="t", comm=sk.COMM_SELF)
+    io.set_outputrate(dt)
+    io.output_fields(src, E, m, 0.0)
+    io.output_fields(src, E, m, 0.5)
+    io.log(1, 0.5, dt)
+    io.finished()
+    d = np.load(tmp_path/"run"/"fields.0001.npz")
+    assert np.array_equal(d["rho"], src.rho.trim()) and np.array_equal(d["Ex"], E['x'].trim())
+    assert d["t"] == 0.5 and np.array_equal(d["x"], m.x)
+    info = pickle.load(open(tmp_path/"run"/"info.p", "rb"))
+    assert info["nx"] == 16 and info["MPI"] == 1 and "seconds" in info
+    assert (tmp_path/"run"/"skeletor.log").exists()

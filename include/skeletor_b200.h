@@ -157,6 +157,15 @@ int skb_deposit(skb_particles_t p, long long np, double *current,
                 const skb_grid_t *grid, int order, double S,
                 const skb_tiling_t *tiling, void *stream);
 
+/* Deterministic deposit (no atomics): needs an exact ordering covering all particles
+ * (tiling->cell_end, n_sorted == np).  Per-cell stencil sums go to cellsums
+ * [ncells][(order+1)^2 * 4] doubles (scratch) and are gathered into `current` in a fixed
+ * order, so the result is a pure function of the stored particle array. */
+int skb_deposit_deterministic(skb_particles_t p, long long np, double *current,
+                              const skb_grid_t *grid, int order, double S,
+                              const skb_tiling_t *tiling, double *cellsums,
+                              void *stream);
+
 /* push_and_deposit_cic/tsc(particles, E, B, qtmh, dt, grid, ihole, current, S,
  *                          update)                   push_and_deposit.pyx:10,91
  * ihole semantics as skb_epilogue_t (unordered list); ihole[0] = -1 flags a
@@ -230,6 +239,13 @@ int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out, long long 
                              const skb_grid_t *grid, int order, int tlx, int tly,
                              int chunk, int *cell_counts, int *block_sums,
                              int *tile_offsets, int *chunk_first_tile, void *stream);
+
+/* Optional: rewrite every cell's particle range (cell_end as left by the sort) in
+ * lexicographic order of (x, y, vx, vy, vz), out of place.  The array then depends only
+ * on the SET of particles: bitwise reproducible, and equal to
+ * np.lexsort((vz, vy, vx, y, x, key)) of the same particles. */
+int skb_canonical_cells(skb_particles_t in, skb_particles_t out, const int *cell_end,
+                        const skb_grid_t *grid, int tlx, int tly, void *stream);
 
 /* ---- guard cells (NumPy slicing in the reference) ----------------------------
  * nc = doubles per cell (1, 3 or 4).

@@ -58,6 +58,7 @@ SIGNATURES = {
                           c_int, c_vp],
     "skb_move_unpack": [_P, c_ll, c_vp, c_int, c_vp, c_int, c_vp, c_vp],
     "skb_deposit": [_P, c_ll, c_vp, _G, c_int, c_dbl, _T, c_vp],
+    "skb_deposit_deterministic": [_P, c_ll, c_vp, _G, c_int, c_dbl, _T, c_vp, c_vp],
     "skb_push_and_deposit": [_P, c_ll, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_vp,
                              c_int, c_vp, c_dbl, c_int, _T, c_vp, c_int, c_int, c_vp],
     "skb_tile_geometry": [_G, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)],
@@ -75,6 +76,7 @@ SIGNATURES = {
     "skb_sort_scatter_rows": [c_vp, c_int, _P, _G, c_int, c_int, c_int, c_vp, c_vp],
     "skb_tile_sort_precounted": [_P, _P, c_ll, _G, c_int, c_int, c_int, c_int, c_vp,
                                  c_vp, c_vp, c_vp, c_vp],
+    "skb_canonical_cells": [_P, _P, c_vp, _G, c_int, c_int, c_vp],
     "skb_copy_guards": [c_vp, c_int, _G, c_vp, c_vp, c_vp],
     "skb_add_guards": [c_vp, c_int, _G, c_int, c_vp, c_vp, c_vp],
     "skb_pack_rows": [c_vp, c_int, _G, c_int, c_int, c_vp, c_vp],
@@ -99,7 +101,7 @@ kernel_launches = 0   # CUDA kernels those calls launched (bench.py's gpu_launch
 
 # kernels launched per C-ABI call (memsets are not counted)
 KERNELS_PER_CALL = {"skb_tile_sort": 6, "skb_calculate_ihole": 3, "skb_move_unpack": 3,
-                    "skb_sort_scan": 4, "skb_sort_clear": 0, "skb_tile_sort_precounted": 5}
+                    "skb_sort_scan": 4, "skb_sort_clear": 0, "skb_tile_sort_precounted": 5, "skb_deposit_deterministic": 2}
 
 
 class SkeletorCudaError(RuntimeError):

@@ -341,11 +341,17 @@ __device__ __forceinline__ void emit_one(double val, int idx, bool in_window, in
     atomicAdd(cur + ((size_t)y * g.mx + x) * 4 + k, val);
 }
 
-template <int ORDER>
+// DET: deterministic variant — no atomics anywhere.  The NS*NS*4 stencil sums of every
+// cell are written to cellsums[cell][NS*NS*4] (zeros for empty cells) and a second
+// kernel (gather_cellsums_kernel) adds them into the source grid in a fixed order, so
+// the result depends only on the (canonically ordered) particle array.
+template <int ORDER, bool DET>
 __global__ void __launch_bounds__(DEP_THREADS)
 deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
-                     DepParams q, int parts, int wstride, int wrows) {
+                     DepParams q, int parts, int wstride, int wrows,
+                     double *__restrict__ cellsums) {
   constexpr int NS = ORDER + 1;
+  constexpr int NV = NS * NS * 4;
   constexpr int UNR = DepUnroll<ORDER>::value;
   extern __shared__ double sw[];
   const int cells_log2 = tl.tlx + tl.tly;
@@ -354,11 +360,17 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
   const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
   const int pbeg = c0 ? tl.cell_end[c0 - 1] : 0;
   const int pend = tl.cell_end[c0 + cpp - 1];
-  if (pbeg == pend) return;                            // uniform: no particles here
-  const Window w = tile_window(tile, tl, g);
-  zero_window(sw, wstride * wrows * 4);
-  __syncthreads();
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  if (pbeg == pend) {                                  // uniform: no particles here
+    if (DET)
+      for (int i = threadIdx.x; i < cpp * NV; i += DEP_THREADS) cellsums[(size_t)c0 * NV + i] = 0.0;
+    return;
+  }
+  const Window w = tile_window(tile, tl, g);
+  if (!DET) {
+    zero_window(sw, wstride * wrows * 4);
+    __syncthreads();
+  }
   const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
   // each warp owns a contiguous block of cells (=> a contiguous particle range); the
   // cell boundaries are fetched 32 at a time, one per lane
@@ -373,7 +385,10 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
       const int s = prev_end;
       const int e = __shfl_sync(SKB_FULL, my_end, j);
       prev_end = e;
-      if (s == e) continue;
+      if (s == e) {
+        if (DET) for (int i = lane; i < NV; i += 32) cellsums[(size_t)(wc0 + cb + j) * NV + i] = 0.0;
+        continue;
+      }
       const int cell = wc0 + cb + j;
       const int local = cell & ((1 << cells_log2) - 1);
       Acc<NS> a;
@@ -405,25 +420,63 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
         }
       }
       // one reduce-scatter per cell; the NS*NS*4 sums land on as many lanes, which
-      // add them to the window in parallel
+      // add them to the window in parallel (or store them, deterministic variant)
       const int lo = (NS == 3) ? 1 : 0;
       const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
                              (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
+      double *cs = DET ? cellsums + (size_t)cell * NV : nullptr;
       if constexpr (NS == 2) {
         warp_reduce_scatter<16>(a.v, lane);
-        if (lane < 16)
-          emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        if (lane < 16) {
+          if (DET) cs[scatter_index<16>(lane)] = a.v[0];
+          else emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        }
       } else {
         warp_reduce_scatter<32>(a.v, lane);
         warp_reduce_scatter<4>(a.v + 32, lane);
-        emit_one<NS>(a.v[0], scatter_index<32>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
-        if (lane < 4)
-          emit_one<NS>(a.v[32], 32 + scatter_index<4>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        if (DET) {
+          cs[scatter_index<32>(lane)] = a.v[0];
+          if (lane < 4) cs[32 + scatter_index<4>(lane)] = a.v[32];
+        } else {
+          emit_one<NS>(a.v[0], scatter_index<32>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+          if (lane < 4)
+            emit_one<NS>(a.v[32], 32 + scatter_index<4>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        }
       }
     }
   }
-  __syncthreads();
-  flush_window(sw, w, wstride, cur, g);
+  if (!DET) {
+    __syncthreads();
+    flush_window(sw, w, wstride, cur, g);
+  }
+}
+
+// Deterministic second phase: every grid cell adds the contributions of the (up to
+// NS*NS) stencil-base cells that reach it, in a fixed order.  One thread per (cell, k).
+template <int NS>
+__global__ void __launch_bounds__(256)
+gather_cellsums_kernel(const double *__restrict__ cellsums, double *__restrict__ cur,
+                       DevGrid g, KeyParams kp) {
+  constexpr int NV = NS * NS * 4;
+  const int lo = (NS == 3) ? 1 : 0;
+  long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)g.mx * g.myp * 4) return;
+  const int k = (int)(idx & 3);
+  const long long cellidx = idx >> 2;
+  const int gy = (int)(cellidx / g.mx), gx = (int)(cellidx - (long long)gy * g.mx);
+  double sum = 0.0;
+#pragma unroll
+  for (int r = 0; r < NS; r++)
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+      const int bx = gx + lo - c, by = gy + lo - r;     // stencil base that reaches (gx, gy)
+      if (bx < 0 || bx >= g.mx || by < 0 || by >= g.myp) continue;
+      const int mxm = (1 << kp.tlx) - 1, mym = (1 << kp.tly) - 1;
+      const int key = ((((by >> kp.tly) * kp.ntx + (bx >> kp.tlx)) << (kp.tlx + kp.tly)) |
+                       ((by & mym) << kp.tlx) | (bx & mxm));
+      sum += cellsums[(size_t)key * NV + (r * NS + c) * 4 + k];
+    }
+  cur[idx] += sum;
 }
 
 // ---------------------------------------------------------------------------------
@@ -632,9 +685,9 @@ static int launch_deposit(skb_particles_t p, long long np, const double *E,
   return 0;
 }
 
-extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
-                           const skb_grid_t *grid, int order, double S,
-                           const skb_tiling_t *tiling, void *stream) {
+static int deposit_impl(skb_particles_t p, long long np, double *current,
+                        const skb_grid_t *grid, int order, double S,
+                        const skb_tiling_t *tiling, double *cellsums, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (np <= 0) return 0;
   DevGrid g = make_grid(grid);
@@ -653,10 +706,24 @@ extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
     while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
     const int ws = window_stride(tl), wr = window_rows(tl);
     const size_t smem = (size_t)ws * wr * 4 * sizeof(double);
+    if (cellsums) {
+      if (np != tl.n_sorted) return (int)cudaErrorInvalidValue;  // needs a full exact order
+      if (order == 1)
+        deposit_cells_kernel<1, true><<<ntiles * parts, DEP_THREADS, 0, st>>>(p, current, g, tl, q, parts, ws, wr, cellsums);
+      else
+        deposit_cells_kernel<2, true><<<ntiles * parts, DEP_THREADS, 0, st>>>(p, current, g, tl, q, parts, ws, wr, cellsums);
+      SKB_CHECK_LAUNCH();
+      KeyParams kp = make_keyparams(g, order, tl.tlx, tl.tly);
+      const unsigned gb = (unsigned)(((long long)g.mx * g.myp * 4 + 255) / 256);
+      if (order == 1) gather_cellsums_kernel<2><<<gb, 256, 0, st>>>(cellsums, current, g, kp);
+      else gather_cellsums_kernel<3><<<gb, 256, 0, st>>>(cellsums, current, g, kp);
+      SKB_CHECK_LAUNCH();
+      return 0;
+    }
     if (order == 1)
-      deposit_cells_kernel<1><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
+      deposit_cells_kernel<1, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);
     else
-      deposit_cells_kernel<2><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
+      deposit_cells_kernel<2, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);
     SKB_CHECK_LAUNCH();
     if (np <= tl.n_sorted) return 0;
     // unsorted tail [n_sorted, np): generic kernel without ordering
@@ -664,9 +731,25 @@ extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
     p.x += n0; p.y += n0; p.vx += n0; p.vy += n0; p.vz += n0;
     np -= n0;
     tl = make_tiling(nullptr);
+  } else if (cellsums) {
+    return (int)cudaErrorInvalidValue;
   }
   if (order == 1) return launch_deposit<1, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
   return launch_deposit<2, 0>(p, np, nullptr, nullptr, current, g, tl, q, fq, st);
+}
+
+extern "C" int skb_deposit(skb_particles_t p, long long np, double *current,
+                           const skb_grid_t *grid, int order, double S,
+                           const skb_tiling_t *tiling, void *stream) {
+  return deposit_impl(p, np, current, grid, order, S, tiling, nullptr, stream);
+}
+
+extern "C" int skb_deposit_deterministic(skb_particles_t p, long long np, double *current,
+                                         const skb_grid_t *grid, int order, double S,
+                                         const skb_tiling_t *tiling, double *cellsums,
+                                         void *stream) {
+  if (!cellsums) return (int)cudaErrorInvalidValue;
+  return deposit_impl(p, np, current, grid, order, S, tiling, cellsums, stream);
 }
 
 extern "C" int skb_push_and_deposit(skb_particles_t p, long long np, const double *E,

@@ -200,6 +200,49 @@ extern "C" int skb_cell_keys(skb_particles_t p, long long np, const skb_grid_t *
   return 0;
 }
 
+// ---- canonical order inside every cell (optional, for bitwise reproducibility) ----
+// The scatter leaves the particles of one cell in claim order, which depends on warp
+// scheduling.  This pass rewrites every cell's range in lexicographic order of
+// (x, y, vx, vy, vz): the stored ARRAY then depends only on the set of particles, so
+// the deposit's summation order — and with it every later bit — is reproducible from
+// run to run and testable against np.lexsort.  One warp per cell; rank by counting
+// (O(n^2 / 32) per cell: n is the number of particles per cell), out of place.
+__device__ __forceinline__ bool row_less(double ax, double ay, double avx, double avy,
+                                         double avz, int ai, double bx, double by,
+                                         double bvx, double bvy, double bvz, int bi) {
+  if (ax != bx) return ax < bx;
+  if (ay != by) return ay < by;
+  if (avx != bvx) return avx < bvx;
+  if (avy != bvy) return avy < bvy;
+  if (avz != bvz) return avz < bvz;
+  return ai < bi;     // identical rows: any order gives the same array
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+canonical_cells_kernel(skb_particles_t in, skb_particles_t out,
+                       const int *__restrict__ cell_end, int ncells) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * SORT_THREADS) >> 5;
+  for (int cell = (blockIdx.x * SORT_THREADS + threadIdx.x) >> 5; cell < ncells;
+       cell += warps) {
+    const int s = cell ? cell_end[cell - 1] : 0;
+    const int e = cell_end[cell];
+    for (int i = s + lane; i < e; i += 32) {
+      const double x = in.x[i], y = in.y[i], vx = in.vx[i], vy = in.vy[i], vz = in.vz[i];
+      int rank = 0;
+      for (int j = s; j < e; j++) {
+        const double xj = in.x[j];            // same address across the warp: broadcast
+        if (xj < x) rank++;
+        else if (xj == x && j != i &&
+                 row_less(xj, in.y[j], in.vx[j], in.vy[j], in.vz[j], j, x, y, vx, vy, vz, i))
+          rank++;
+      }
+      const int d = s + rank;
+      out.x[d] = x; out.y[d] = y; out.vx[d] = vx; out.vy[d] = vy; out.vz[d] = vz;
+    }
+  }
+}
+
 // AoS rows (migration arrivals): histogram / scatter into the sorted SoA arrays
 __global__ void __launch_bounds__(SORT_THREADS)
 count_rows_kernel(const double *__restrict__ rows, int n, KeyParams kp, int *counts) {
@@ -330,5 +373,19 @@ extern "C" int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out,
     scatter_kernel<<<sblk, SORT_THREADS, 0, st>>>(in, out, np, kp, cell_counts);
     SKB_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+extern "C" int skb_canonical_cells(skb_particles_t in, skb_particles_t out,
+                                   const int *cell_end, const skb_grid_t *grid, int tlx,
+                                   int tly, void *stream) {
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  const int ncells = (ntx * nty) << (tlx + tly);
+  int blocks = (ncells + (SORT_THREADS / 32) - 1) / (SORT_THREADS / 32);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  canonical_cells_kernel<<<blocks, SORT_THREADS, 0, (cudaStream_t)stream>>>(in, out,
+                                                                          cell_end, ncells);
+  SKB_CHECK_LAUNCH();
   return 0;
 }

@@ -142,6 +142,7 @@ class Particles:
         self._n_sorted = 0
         self._sorted = False
         self.sort_enabled = True
+        self.deterministic = False    # canonical intra-cell order after every sort
         self.fused_push = False   # two-pass recompute path: correct, but the push is
         # instruction-bound, so it is not faster than push + precounted sort
 
@@ -249,8 +250,23 @@ class Particles:
                       self._tile_offsets.data_ptr(), self._chunk_first.data_ptr(), 0,
                       None, _stream())
         self._data, self._alt = self._alt, self._data
+        if self.deterministic:
+            # claim order inside a cell depends on warp scheduling: rewrite every cell
+            # in lexicographic order so the stored array (and every deposit sum that
+            # follows) is bitwise reproducible
+            _lib.call("skb_canonical_cells", self._c, self._soa(self._alt),
+                      self._cell_counts.data_ptr(), self.manifold.c, TLX, TLY, _stream())
+            self._data, self._alt = self._alt, self._data
         self._n_sorted = self.N
         self._sorted = True
+
+    def _cellsums(self):
+        """scratch of the deterministic deposit: [ncells][(order+1)^2 * 4] doubles"""
+        if getattr(self, "_cellsums_buf", None) is None:
+            nv = (self.order + 1)**2*4
+            self._cellsums_buf = torch.zeros((self._cell_counts.numel() - 1)*nv,
+                                             dtype=torch.float64, device=self.device)
+        return self._cellsums_buf
 
     def _ensure_sorted(self):
         if not self._sorted:

@@ -40,8 +40,13 @@ class Sources(Field):
         # Rate of shear
         S = getattr(self.grid, 'S', 0.0)
         particles._ensure_sorted()
-        _lib.call("skb_deposit", particles._c, particles.N, self.ptr, self.grid.c,
-                  particles.order, float(S), particles._tiling_c(), _stream())
+        if particles.deterministic and particles._sorted and particles.N > 0:
+            _lib.call("skb_deposit_deterministic", particles._c, particles.N, self.ptr,
+                      self.grid.c, particles.order, float(S), particles._tiling_c(),
+                      particles._cellsums().data_ptr(), _stream())
+        else:
+            _lib.call("skb_deposit", particles._c, particles.N, self.ptr, self.grid.c,
+                      particles.order, float(S), particles._tiling_c(), _stream())
         self.boundaries_set = False
         self.normalize(particles)
         if set_boundaries:

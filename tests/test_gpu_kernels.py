@@ -651,3 +651,52 @@ def test_error_behaviour_matches_reference():
     f.copy_guards()
     with pytest.raises(AssertionError):
         f.copy_guards()                            # field.py:106
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_deterministic_mode_is_bitwise_reproducible_and_canonical(order):
+    """Particles.deterministic: after every sort the stored array equals
+    np.lexsort((vz, vy, vx, y, x, key)) of the oracle's particles — the sort permutation
+    is exact — and deposits are bitwise identical from run to run"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 32, 32, 40
+    g = orc.Grid(nx, ny, lbx=2, lby=2)
+    rng = np.random.default_rng(41)
+    n = nx*ny*npc
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    # a few exactly coincident positions (quiet-start like): ties in x and y
+    x[:200] = x[200:400]
+    y[:100] = y[200:300]
+    v = rng.normal(0, 0.5, (3, n))
+    E = random_field(g, orc.Float3, rng, -0.2, 0.2)
+    B = random_field(g, orc.Float3, rng)
+    dt = 0.4*g.dx
+    runs = []
+    for rep in range(2):
+        m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
+        ions = sk.Particles(m, int(1.3*n), order=order)
+        ions.deterministic = True
+        ions.initialize(x, y, v[0], v[1], v[2])
+        Ef, Bf = sk.Field(m, dtype=sk.Float3), sk.Field(m, dtype=sk.Float3)
+        Ef[...] = E
+        Bf[...] = B
+        src = sk.Sources(m)
+        for it in range(3):
+            ions.push(Ef, Bf, dt)
+            src.deposit(ions, set_boundaries=True)
+        runs.append((np.asarray(ions[:ions.N]).copy(), np.asarray(src).copy()))
+    assert np.array_equal(bits(runs[0][0]), bits(runs[1][0]))
+    assert np.array_equal(bits(runs[0][1]), bits(runs[1][1]))        # bitwise deposits
+    # oracle: same particles, canonical order
+    p = np.zeros(int(1.3*n), orc.Particle)
+    p["x"][:n], p["y"][:n] = x/g.dx, y/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = v
+    parts, N = [p], [n]
+    for it in range(3):
+        orc.push(parts[0][:N[0]], E, B, g, order, 1.0*dt/2, dt)
+        parts, N = orc.move(parts, N, [g])
+        orc.periodic_x(parts[0][:N[0]], g)
+    q = parts[0][:N[0]]
+    key = orc.cell_keys(q, g, order, (4, 4))
+    perm = np.lexsort((q["vz"], q["vy"], q["vx"], q["y"], q["x"], key))
+    assert np.array_equal(bits(runs[0][0]), bits(q[perm]))

@@ -119,8 +119,9 @@ int skb_calculate_ihole(skb_particles_t p, long long np, int *ihole, int ntmax,
 /* ---- particle manager: cppmove2(particles, npp, sbufl, sbufr, rbufl, rbufr,
  *      ihole, info, grid)           ppic2_wrapper.pyx:51-67, pplib2.c:607-981
  * split into its two local halves; the neighbour exchange between them
- * (MPI_Isend/Irecv, pplib2.c:741-753) is done by the caller (NCCL send/recv, or
- * a device copy when nvp == 1).
+ * (MPI_Isend/Irecv, pplib2.c:741-753) is done by the caller (copies into the
+ * neighbours' NVLink peer-memory slots, NCCL send/recv as fallback, or a device copy
+ * when nvp == 1).
  *
  * skb_move_pack: for each listed hole, copy the particle into sbufl (y <
  *   edges[0]; y += ny if rank == 0, pplib2.c:676-677) or sbufr (otherwise; y -=
@@ -197,7 +198,8 @@ int skb_tile_sort(skb_particles_t in, skb_particles_t out, long long np,
                   int *cell_counts, int *block_sums, int *tile_offsets,
                   int *chunk_first_tile, int stable, int *perm, void *stream);
 
-/* ---- fused push + tile sort (B200-native fast path of Particles.push) ----------
+/* ---- fused push + tile sort (alternative to push + skb_tile_sort_precounted; correct
+ * and tested, but not faster on B200 because the push is instruction-bound) ------
  * Two passes that both recompute the push from the OLD particle state:
  * skb_push_count:   pass 1 — push in registers; particles that leave the slab are
  *   packed into sbufl / sbufr exactly as skb_move_pack would (counts[0], counts[1],

@@ -5,13 +5,19 @@ import numpy as np
 
 class InitialCondition:
 
-    def __init__(self, npc, quiet=False, vt=0.0, global_init=False):
+    def __init__(self, npc, quiet=False, vt=0.0, global_init=False, on_device=False,
+                 seed=None):
         # Quiet start / particles per cell / ion thermal velocity /
         # initialize particles "globally" on each processor?
         self.quiet = quiet
         self.npc = npc
         self.vt = vt
         self.global_init = global_init
+        # extension: draw the (noisy start) coordinates with the GPU's generator straight
+        # into device memory — needed to even start a 1e9-particle run (the host path
+        # is kept as the default because the reference's tests seed np.random)
+        self.on_device = on_device
+        self.seed = seed
 
     def positions(self, nx, ny):
         N = nx*ny*self.npc
@@ -28,7 +34,24 @@ class InitialCondition:
             y = ny*np.random.uniform(size=N)
         return x, y
 
+    def _call_on_device(self, manifold, ions):
+        import torch
+        assert not self.quiet and not self.global_init, \
+            "on_device supports the noisy per-slab start only"
+        N = manifold.nx*manifold.nyp*self.npc
+        gen = torch.Generator(device=ions.device)
+        gen.manual_seed((self.seed if self.seed is not None else 0) + manifold.comm.rank)
+        kw = dict(generator=gen, device=ions.device, dtype=torch.float64)
+        d = ions._data
+        d[0, :N] = torch.rand(N, **kw)*manifold.nx
+        d[1, :N] = torch.rand(N, **kw)*manifold.nyp + manifold.edges[0]
+        d[2:5, :N] = torch.randn((3, N), **kw)*self.vt
+        ions.N = N
+        ions._sorted = False
+
     def __call__(self, manifold, ions):
+        if self.on_device:
+            return self._call_on_device(manifold, ions)
         nx = manifold.nx
         ny = manifold.ny if self.global_init else manifold.nyp
         N = nx*ny*self.npc

@@ -79,6 +79,9 @@ class Particles:
         assert manifold.lbx >= order//2 + 1, msg
 
         Nmax = int(Nmax)
+        # particle indices are 32-bit on the device (like the reference's C ints,
+        # pplib2.c:673), one slab holds at most ~2.1e9 particles
+        assert Nmax < 2**31 - 2**20, "Nmax too large for one slab: use more ranks"
         # Size of buffer for passing particles between processors
         nbmax = int(max(0.1*Nmax, 1)) if nbmax is None else int(max(nbmax, 1))
         # Size of ihole buffer for particles leaving processor

@@ -310,3 +310,18 @@ def test_io_snapshots(tmp_path, monkeypatch):
     info = pickle.load(open(tmp_path/"run"/"info.p", "rb"))
     assert info["nx"] == 16 and info["MPI"] == 1 and "seconds" in info
     assert (tmp_path/"run"/"skeletor.log").exists()
+
+
+def test_on_device_initial_condition():
+    import skeletor_b200 as sk
+    m = sk.Manifold(64, 32, sk.COMM_SELF)
+    npc = 32
+    ions = sk.Particles(m, int(1.5*64*32*npc))
+    sk.InitialCondition(npc, vt=0.3, on_device=True, seed=7)(m, ions)
+    assert ions.N == 64*32*npc
+    p = np.asarray(ions[:ions.N])
+    assert (p['x'] >= 0).all() and (p['x'] < 64).all() and (p['y'] >= 0).all() and (p['y'] < 32).all()
+    assert abs(p['vx'].std() - 0.3) < 0.01 and abs(p['x'].mean() - 32) < 0.5
+    src = sk.Sources(m)
+    src.deposit(ions, set_boundaries=True)
+    assert np.isclose(src.rho.trim().sum(), 64*32)

@@ -94,8 +94,10 @@ __device__ __forceinline__ void push_one(const double *sE, const double *sB, con
   if (q.flags) boundary_epilogue(q, g, i, x, y, vx);
 }
 
+// resident CTAs per SM the register allocation aims for: 3 for CIC (80 registers, no
+// spills), 2 for TSC (118); measured best on B200
 template <int ORDER, bool MODIFIED>
-__global__ void __launch_bounds__(PUSH_THREADS)
+__global__ void __launch_bounds__(PUSH_THREADS, (ORDER == 1) ? 3 : 2)
 push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
             const double *__restrict__ B, DevGrid g, DevTiling tl, PushParams q,
             int span, int wstride, int wrows) {

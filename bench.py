@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--ny", type=int, default=NY)
     ap.add_argument("--ppc", type=int, default=PPC)
     ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: ny grows with the GPU count (ny rows PER GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -377,8 +379,8 @@ def b200_arm(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms/a.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak" if a.weak else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(a, {"particles_per_gpu": n_local}),
                 "roofline": roofline, "kernels": kern, "alternative_kernels": standalone, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}
@@ -387,6 +389,8 @@ def b200_arm(a):
 
 def main():
     a = parse()
+    if a.weak:
+        a.ny = a.ny*max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if a.impl == "reference":
         reference_arm(a)
     else:

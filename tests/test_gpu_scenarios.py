@@ -105,3 +105,46 @@ def test_user_writes_keep_working():
     assert np.array_equal(np.asarray(ions[:10]['x']), np.arange(10) + 0.5)
     src.deposit(ions, set_boundaries=True)
     assert np.isclose(src.rho.trim().sum(), 32*32)
+
+
+def test_reference_style_script_runs_through_compat_imports(tmp_path):
+    """compat/: `from skeletor import ...` + `from mpi4py.MPI import COMM_WORLD` (the
+    imports of every reference test) resolve to the B200 path; run in a subprocess so the
+    names do not clash with the oracle's serial mpi4py stand-in"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ref_style.py"
+    script.write_text('''
+from skeletor import Float3, Field, Particles, Sources, Ohm, InitialCondition
+from skeletor.manifolds.second_order import Manifold
+import numpy as np
+from mpi4py import MPI
+from mpi4py.MPI import COMM_WORLD as comm
+
+nx, ny, npc = 32, 32, 16
+manifold = Manifold(nx, ny, comm, Lx=1.0, Ly=1.0)
+N = npc*nx*ny
+ions = Particles(manifold, int(1.5*N/comm.size), charge=0.5, mass=1.0)
+InitialCondition(npc, quiet=True)(manifold, ions)
+x = ions['x']*manifold.dx
+ions['vx'] = 1e-3*np.sin(2*np.pi*x)
+assert comm.allreduce(ions.N, op=MPI.SUM) == N
+E = Field(manifold, dtype=Float3); E.fill((0.0, 0.0, 0.0)); E.copy_guards()
+B = Field(manifold, dtype=Float3); B.fill((0.0, 0.0, 0.0)); B.copy_guards()
+sources = Sources(manifold)
+ohm = Ohm(manifold, temperature=1.0, charge=0.5)
+for it in range(5):
+    ions.push(E, B, 0.5*manifold.dx)
+    sources.deposit(ions)
+    sources.add_guards()
+    sources.copy_guards()
+    ohm(sources, B, E)
+    E.copy_guards()
+assert np.isclose(comm.allreduce(sources.rho.trim().sum(), op=MPI.SUM), N*0.5/npc)
+print("compat OK")
+''')
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), root]))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True,
+                       env=env, timeout=300)
+    assert r.returncode == 0 and "compat OK" in r.stdout, r.stderr[-2000:]

@@ -6,14 +6,19 @@
 // through the optional epilogue, shear_periodic_y / periodic_x / calculate_ihole
 // (particle_boundary.pyx:5-49).
 //
-// Design: one CTA per work item of `span` consecutive particles.  Particles are
-// tile-ordered (skb_tile_sort), so a work item covers one or a few tiles; for each
-// the CTA stages the (tile + halo) window of E and B (interleaved x,y,z, as in
-// HBM) in shared memory with coalesced 128-bit row copies and gathers from there.
-// A particle whose stencil is not inside the window (stale ordering, unsorted
-// tail) gathers from global memory instead — ordering is a performance property,
-// never a correctness requirement.  Particle traffic is 5 coalesced double loads +
-// 5 stores = 80 B/particle, the algorithmic minimum.
+// Design: one CTA per work item of `span` (16384) consecutive particles.  Particles
+// are tile-ordered (skb_tile_sort), so a work item covers one or a few tiles; for
+// each the CTA stages the (tile + halo) window of E and B (interleaved x,y,z, as in
+// HBM) in shared memory, one warp per row, and gathers from there.  A particle whose
+// stencil is not inside the window (stale ordering, unsorted tail) gathers from
+// global memory instead — ordering is a performance property, never a correctness
+// requirement.  The particle coordinates of the NEXT iteration arrive through a
+// two-deep cp.async ring in shared memory (no registers held while the load is in
+// flight) and the lines of the iteration after that are prefetched into L2.
+// Particle traffic is 5 coalesced 8-byte loads + 5 stores = 80 B/particle, the
+// algorithmic minimum.  The optional epilogue folds shear_periodic_y, periodic_x,
+// calculate_ihole and the first pass of the tile sort (histogram of the NEW cell
+// keys) into the same pass.
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -39,15 +44,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-#define PUSH_THREADS_ 256
+// slot layout of the ring: [2 buffers][5 coordinates][PUSH_THREADS]
 __device__ __forceinline__ void async_load_particle(double *pbuf, int buf, const skb_particles_t &P,
                                                     long long i) {
-  double *d = pbuf + buf * 5 * PUSH_THREADS_ + threadIdx.x;
+  double *d = pbuf + buf * 5 * PUSH_THREADS + threadIdx.x;
   cp_async8(d, P.x + i);
-  cp_async8(d + PUSH_THREADS_, P.y + i);
-  cp_async8(d + 2 * PUSH_THREADS_, P.vx + i);
-  cp_async8(d + 3 * PUSH_THREADS_, P.vy + i);
-  cp_async8(d + 4 * PUSH_THREADS_, P.vz + i);
+  cp_async8(d + PUSH_THREADS, P.y + i);
+  cp_async8(d + 2 * PUSH_THREADS, P.vx + i);
+  cp_async8(d + 3 * PUSH_THREADS, P.vy + i);
+  cp_async8(d + 4 * PUSH_THREADS, P.vz + i);
 }
 
 struct PushParams {

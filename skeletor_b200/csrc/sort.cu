@@ -218,28 +218,90 @@ __device__ __forceinline__ bool row_less(double ax, double ay, double avx, doubl
   return ai < bi;     // identical rows: any order gives the same array
 }
 
+#define CANON_MAX 1024   // cells up to this many particles are sorted in shared memory
+
+__device__ __forceinline__ unsigned long long sortable_bits(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // total order == numeric order
+}
+
+// rank-by-counting fallback for very crowded cells (n > CANON_MAX): O(n^2 / 32)
+__device__ __forceinline__ void canonical_by_counting(const skb_particles_t &in,
+                                                      const skb_particles_t &out, int s,
+                                                      int e, int lane) {
+  for (int i = s + lane; i < e; i += 32) {
+    const double x = in.x[i], y = in.y[i], vx = in.vx[i], vy = in.vy[i], vz = in.vz[i];
+    int rank = 0;
+    for (int j = s; j < e; j++) {
+      const double xj = in.x[j];
+      if (xj < x) rank++;
+      else if (xj == x && j != i &&
+               row_less(xj, in.y[j], in.vx[j], in.vy[j], in.vz[j], j, x, y, vx, vy, vz, i))
+        rank++;
+    }
+    const int d = s + rank;
+    out.x[d] = x; out.y[d] = y; out.vx[d] = vx; out.vy[d] = vy; out.vz[d] = vz;
+  }
+}
+
+// One warp per cell: bitonic sort of (sortable x bits, local index) pairs in shared
+// memory; ties in x (quiet starts put many particles on the same x) are resolved by
+// comparing the remaining coordinates from global memory.
 __global__ void __launch_bounds__(SORT_THREADS)
 canonical_cells_kernel(skb_particles_t in, skb_particles_t out,
                        const int *__restrict__ cell_end, int ncells) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ unsigned long long canon_smem[];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  unsigned long long *keys = canon_smem + (size_t)wv * CANON_MAX;
+  int *idx = (int *)(canon_smem + (size_t)(SORT_THREADS / 32) * CANON_MAX) + wv * CANON_MAX;
   const int warps = (gridDim.x * SORT_THREADS) >> 5;
   for (int cell = (blockIdx.x * SORT_THREADS + threadIdx.x) >> 5; cell < ncells;
        cell += warps) {
     const int s = cell ? cell_end[cell - 1] : 0;
     const int e = cell_end[cell];
-    for (int i = s + lane; i < e; i += 32) {
-      const double x = in.x[i], y = in.y[i], vx = in.vx[i], vy = in.vy[i], vz = in.vz[i];
-      int rank = 0;
-      for (int j = s; j < e; j++) {
-        const double xj = in.x[j];            // same address across the warp: broadcast
-        if (xj < x) rank++;
-        else if (xj == x && j != i &&
-                 row_less(xj, in.y[j], in.vx[j], in.vy[j], in.vz[j], j, x, y, vx, vy, vz, i))
-          rank++;
+    const int n = e - s;
+    if (n <= 0) continue;
+    if (n == 1) {
+      if (lane == 0) {
+        out.x[s] = in.x[s]; out.y[s] = in.y[s]; out.vx[s] = in.vx[s];
+        out.vy[s] = in.vy[s]; out.vz[s] = in.vz[s];
       }
-      const int d = s + rank;
-      out.x[d] = x; out.y[d] = y; out.vx[d] = vx; out.vy[d] = vy; out.vz[d] = vz;
+      continue;
     }
+    if (n > CANON_MAX) { canonical_by_counting(in, out, s, e, lane); continue; }
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int t = lane; t < P; t += 32) {
+      keys[t] = (t < n) ? sortable_bits(in.x[s + t]) : ~0ull;   // padding sorts last
+      idx[t] = t;
+    }
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (P >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int l = i | j;
+          const bool asc = (i & k) == 0;
+          const unsigned long long ki = keys[i], kl = keys[l];
+          const int ii = idx[i], il = idx[l];
+          bool gt;                       // element i sorts after element l ?
+          if (ki != kl) gt = ki > kl;
+          else if (ii >= n || il >= n) gt = ii > il;   // padding vs padding / tie
+          else {
+            const int a = s + ii, b = s + il;
+            gt = row_less(in.x[b], in.y[b], in.vx[b], in.vy[b], in.vz[b], il,
+                          in.x[a], in.y[a], in.vx[a], in.vy[a], in.vz[a], ii);
+          }
+          if (gt == asc) { keys[i] = kl; keys[l] = ki; idx[i] = il; idx[l] = ii; }
+        }
+        __syncwarp();
+      }
+    for (int t = lane; t < n; t += 32) {
+      const int src = s + idx[t], d = s + t;
+      out.x[d] = in.x[src]; out.y[d] = in.y[src]; out.vx[d] = in.vx[src];
+      out.vy[d] = in.vy[src]; out.vz[d] = in.vz[src];
+    }
+    __syncwarp();
   }
 }
 
@@ -383,9 +445,13 @@ extern "C" int skb_canonical_cells(skb_particles_t in, skb_particles_t out,
   skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
   const int ncells = (ntx * nty) << (tlx + tly);
   int blocks = (ncells + (SORT_THREADS / 32) - 1) / (SORT_THREADS / 32);
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  canonical_cells_kernel<<<blocks, SORT_THREADS, 0, (cudaStream_t)stream>>>(in, out,
-                                                                          cell_end, ncells);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const size_t smem = (size_t)(SORT_THREADS / 32) * CANON_MAX * (sizeof(unsigned long long) + sizeof(int));
+  cudaError_t e = cudaFuncSetAttribute(canonical_cells_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  canonical_cells_kernel<<<blocks, SORT_THREADS, smem, (cudaStream_t)stream>>>(in, out,
+                                                                             cell_end, ncells);
   SKB_CHECK_LAUNCH();
   return 0;
 }

@@ -700,3 +700,23 @@ def test_deterministic_mode_is_bitwise_reproducible_and_canonical(order):
     key = orc.cell_keys(q, g, order, (4, 4))
     perm = np.lexsort((q["vz"], q["vy"], q["vx"], q["y"], q["x"], key))
     assert np.array_equal(bits(runs[0][0]), bits(q[perm]))
+
+
+@pytest.mark.parametrize("npc", [3, 700, 2500])
+def test_canonical_cells_matches_lexsort(npc):
+    """skb_canonical_cells: sparse cells, shared-memory bitonic path (n <= 1024) and the
+    counting fallback for very crowded cells, with many exact ties in x"""
+    g = orc.Grid(nx=8, ny=8, lbx=2, lby=2)
+    rng = np.random.default_rng(51)
+    n = 64*npc
+    p = random_particles(g, n, rng)
+    p["x"][: n//2] = np.floor(p["x"][: n//2]*4)/4 + 0.125      # lattice-like ties in x
+    tl = gu.Tiling(g, 1)
+    t = tl.sort(gu.soa(p), n)
+    out = torch.zeros_like(t)
+    _lib.call("skb_canonical_cells", gu.cparts(t), gu.cparts(out), tl.cell_counts.data_ptr(),
+              gu.cgrid(g), 4, 4, gu.stream())
+    got = gu.aos(out, n)
+    key = orc.cell_keys(p, g, 1, (4, 4))
+    perm = np.lexsort((p["vz"], p["vy"], p["vx"], p["y"], p["x"], key))
+    assert np.array_equal(bits(got), bits(p[perm]))

@@ -1,7 +1,6 @@
 """Sources: charge and current density (rho, Jx, Jy, Jz) deposited from particles.
 
 Mirrors skeletor.Sources (reference skeletor/sources.py:5-192)."""
-import torch
 
 from . import _lib
 from .field import Field, _stream

@@ -2,7 +2,6 @@
 skeletor/time_steppers/horowitz.py, predictor_corrector.py)."""
 import math
 
-import torch
 
 from ..faraday import Faraday
 from ..field import Field

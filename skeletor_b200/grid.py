@@ -1,5 +1,9 @@
-"""Grid: slab geometry of the y-decomposed domain (reference skeletor/grid.py:5-85,
-grid_t in skeletor/cython/types.pxd:25-37)."""
+"""Grid: geometry of one y-slab of the decomposed domain.
+
+Attribute names and meaning follow the reference (skeletor/grid.py:5-85 and the
+`grid_t` extension type, skeletor/cython/types.pxd:25-37); `Grid.c` packs them into the
+`skb_grid_t` POD of the C ABI.
+"""
 import numpy as np
 
 from . import _lib
@@ -9,56 +13,45 @@ class Grid:
 
     def __init__(self, nx, ny, comm,
                  lbx=1, lby=1, Lx=1.0, Ly=1.0, x0=0.0, y0=0.0):
-        # Number of grid points in x- and y-direction
-        self.nx = nx
-        self.ny = ny
-        # Grid size, origin, cell size
-        self.Lx = Lx
-        self.Ly = Ly
-        self.x0 = x0
-        self.y0 = y0
-        self.dx = self.Lx/self.nx
-        self.dy = self.Ly/self.ny
-        # communicator (mpi4py-like: skeletor_b200.comm)
-        self.comm = comm
-        # nyp = number of grid rows in this slab, noff = first global row
+        if comm.size > ny:
+            msg = "Too many processors requested: ny={}, comm.size={}"
+            raise RuntimeError(msg.format(ny, comm.size))
+        self.comm = comm                       # mpi4py-like: skeletor_b200.comm
+        # global box: cells, physical size, origin, cell size
+        self.nx, self.ny = nx, ny
+        self.Lx, self.Ly = Lx, Ly
+        self.x0, self.y0 = x0, y0
+        self.dx, self.dy = Lx/nx, Ly/ny
+        # this rank's slab: nyp rows starting at global row noff; particles live in
+        # edges[0] <= y < edges[1] (floats, compared against particle y directly)
         self.nyp = ny//comm.size
         self.noff = self.nyp*comm.rank
-        # edges[0:1] = lower:upper boundary of particle partition (floats)
         self.edges = [float(self.noff), float(self.noff + self.nyp)]
-        # first active index / first upper guard index
-        self.lbx = lbx
-        self.ubx = lbx + self.nx
-        self.lby = lby
-        self.uby = lby + self.nyp
-        # total (active plus guard) number of grid points in each subdomain
-        self.mx = self.nx + 2*self.lbx
-        self.myp = self.nyp + 2*self.lby
-
-        if comm.size > self.ny:
-            msg = "Too many processors requested: ny={}, comm.size={}"
-            raise RuntimeError(msg.format(self.ny, comm.size))
+        # guard layers: lb* = index of the first active cell, ub* = first upper guard
+        self.lbx, self.lby = lbx, lby
+        self.ubx, self.uby = lbx + nx, lby + self.nyp
+        # extent of the stored arrays, guards included
+        self.mx, self.myp = nx + 2*lbx, self.nyp + 2*lby
         # the guard-cell kernels fold / copy whole guard layers in one pass
-        assert self.nx >= 2*self.lbx and self.nyp >= self.lby, \
-            "slab too small for its guard layers"
+        assert nx >= 2*lbx and self.nyp >= lby, "slab too small for its guard layers"
+
+    def _centres(self, first, count, origin, spacing):
+        return origin + (np.arange(first, first + count) + 0.5)*spacing
 
     @property
     def x(self):
-        "One-dimensional x-coordinate array"
-        return self.x0 + (np.arange(self.nx) + 0.5)*self.dx
+        "cell-centre x coordinates of the active cells"
+        return self._centres(0, self.nx, self.x0, self.dx)
 
     @property
     def y(self):
-        "One-dimensional y-coordinate array"
-        yrange = np.arange(self.noff, self.noff + self.nyp)
-        return self.y0 + (yrange + 0.5)*self.dy
+        "cell-centre y coordinates of this slab's active rows"
+        return self._centres(self.noff, self.nyp, self.y0, self.dy)
 
     @property
     def yg(self):
-        "One-dimensional y-coordinate array including ghost"
-        yrange = np.arange(self.noff - self.lby,
-                           self.noff + self.nyp + self.lby)
-        return self.y0 + (yrange + 0.5)*self.dy
+        "cell-centre y coordinates of this slab's rows including the guard rows"
+        return self._centres(self.noff - self.lby, self.myp, self.y0, self.dy)
 
     @property
     def c(self):

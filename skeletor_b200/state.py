@@ -1,12 +1,11 @@
+"""State handed to the time steppers (reference skeletor/state.py)."""
+
+
 class State:
+    """Particle species + magnetic field + time.  `species` may be one Particles object
+    or a list of them; it is always stored as a list."""
 
     def __init__(self, species, B, time=0.0):
-        """State class (reference skeletor/state.py:1-17).
-        species: list of Particles objects or a single Particles object (stored
-        as a one-element list)."""
-        if isinstance(species, list):
-            self.species = species
-        else:
-            self.species = [species]
+        self.species = species if isinstance(species, list) else [species]
         self.B = B
         self.t = time

@@ -720,3 +720,46 @@ def test_canonical_cells_matches_lexsort(npc):
     key = orc.cell_keys(p, g, 1, (4, 4))
     perm = np.lexsort((p["vz"], p["vy"], p["vx"], p["y"], p["x"], key))
     assert np.array_equal(bits(got), bits(p[perm]))
+
+
+def test_sort_disabled_path_matches_oracle():
+    """Particles.sort_enabled = False: push / deposit through the unordered (global
+    memory) paths — same particles and sources as the oracle"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 32, 32, 12
+    g = orc.Grid(nx, ny, lbx=1, lby=1)
+    rng = np.random.default_rng(61)
+    n = nx*ny*npc
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    v = rng.normal(0, 0.5, (3, n))
+    E = random_field(g, orc.Float3, rng, -0.2, 0.2)
+    B = random_field(g, orc.Float3, rng)
+    dt = 0.4*g.dx
+    m = sk.Manifold(nx, ny, sk.COMM_SELF)
+    ions = sk.Particles(m, int(1.3*n))
+    ions.sort_enabled = False
+    ions.initialize(x, y, v[0], v[1], v[2])
+    Ef, Bf = sk.Field(m, dtype=sk.Float3), sk.Field(m, dtype=sk.Float3)
+    Ef[...] = E
+    Bf[...] = B
+    src = sk.Sources(m)
+    for it in range(3):
+        ions.push(Ef, Bf, dt)
+    assert not ions._sorted
+    src.deposit(ions, set_boundaries=True)
+    p = np.zeros(int(1.3*n), orc.Particle)
+    p["x"][:n], p["y"][:n] = x/g.dx, y/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = v
+    parts, N = [p], [n]
+    for it in range(3):
+        orc.push(parts[0][:N[0]], E, B, g, 1, 1.0*dt/2, dt)
+        parts, N = orc.move(parts, N, [g])
+        orc.periodic_x(parts[0][:N[0]], g)
+    so = g.field(orc.Float4)
+    orc.deposit(parts[0][:N[0]], so, g, 1)
+    orc.normalize([so], [g], N, 1.0, 1.0)
+    orc.add_guards([so], [g])
+    orc.copy_guards([so], [g])
+    assert np.array_equal(gu.sorted_rows(np.asarray(ions[:ions.N])),
+                          gu.sorted_rows(parts[0][:N[0]]))
+    assert rel(np.asarray(src), so) < 1e-12

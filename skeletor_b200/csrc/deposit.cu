@@ -272,6 +272,13 @@ deposit_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
 // ahead of their use to keep enough bytes in flight with only 16 resident warps.
 // A particle whose stencil base is not the cell it is filed under (caller passed a
 // stale ordering) is deposited on its own through HBM atomics: correct, just slow.
+#ifndef DEP_PREFETCH_LINES
+#define DEP_PREFETCH_LINES 16   // 16 lines x 16 doubles = the next 256 particles
+#endif
+__device__ __forceinline__ void dep_prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int ORDER> struct DepUnroll { static constexpr int value = (ORDER == 1) ? 4 : 2; };
 
 template <int NS>
@@ -385,6 +392,16 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
       const int s = prev_end;
       const int e = __shfl_sync(SKB_FULL, my_end, j);
       prev_end = e;
+      {
+        // pull the particles that follow this cell (the warp's next cells) into L2
+        // while this one is being reduced: 128-byte lines, one per lane and array
+        const int ahead = e + lane * 16;
+        if (ahead < min(e + 16 * DEP_PREFETCH_LINES, pend)) {
+          dep_prefetch_l2(P.x + ahead); dep_prefetch_l2(P.y + ahead);
+          dep_prefetch_l2(P.vx + ahead); dep_prefetch_l2(P.vy + ahead);
+          dep_prefetch_l2(P.vz + ahead);
+        }
+      }
       if (s == e) {
         if (DET) for (int i = lane; i < NV; i += 32) cellsums[(size_t)(wc0 + cb + j) * NV + i] = 0.0;
         continue;

@@ -573,6 +573,15 @@ pd_cells_kernel(skb_particles_t P, const double *__restrict__ E,
       const int s = prev_end;
       const int e = __shfl_sync(SKB_FULL, my_end, j);
       prev_end = e;
+      {
+        // pull the particles that follow this cell into L2 (see deposit_cells_kernel)
+        const int ahead = e + lane * 16;
+        if (ahead < min(e + 16 * DEP_PREFETCH_LINES, pend)) {
+          dep_prefetch_l2(P.x + ahead); dep_prefetch_l2(P.y + ahead);
+          dep_prefetch_l2(P.vx + ahead); dep_prefetch_l2(P.vy + ahead);
+          dep_prefetch_l2(P.vz + ahead);
+        }
+      }
       if (s == e) continue;
       const int local = (wc0 + cb + j) & ((1 << cells_log2) - 1);
       Acc<NS> a;

@@ -13,8 +13,11 @@ __device__ __forceinline__ void load_stencil(const double *__restrict__ sw,
                                              double (&v)[NS * NS][3]) {
   const int lo = (NS == 3) ? 1 : 0;
   const int x_lo = ix - lo, y_lo = iy - lo;
-  if (x_lo >= w.x0 && x_lo + NS <= w.x1 && y_lo >= w.y0 && y_lo + NS <= w.y1) {
-    const double *b = sw + ((size_t)(y_lo - w.y0) * wstride + (x_lo - w.x0)) * 3;
+  // x_lo in [w.x0, w.x1 - NS] and y_lo in [w.y0, w.y1 - NS]: one unsigned compare each
+  const unsigned rx = (unsigned)(x_lo - w.x0), ry = (unsigned)(y_lo - w.y0);
+  if (rx <= (unsigned)(w.x1 - w.x0 - NS) && ry <= (unsigned)(w.y1 - w.y0 - NS) &&
+      w.x1 - w.x0 >= NS && w.y1 - w.y0 >= NS) {
+    const double *b = sw + ((size_t)ry * wstride + rx) * 3;
 #pragma unroll
     for (int a = 0; a < NS; a++)
 #pragma unroll

@@ -69,24 +69,28 @@ struct PushParams {
 // shear_periodic_y + calculate_ihole + periodic_x for one particle
 // (particle_boundary.pyx:26-49, pxd:10-22, pxd:3-7; order as Particles.push,
 // particles.py:181-188: shear boost, hole detection, then x wrap)
+// FLAGS >= 0: the epilogue flags are compile-time constants (the production
+// combinations get their own kernel instances); FLAGS < 0: read q.flags at run time.
+template <int FLAGS = -1>
 __device__ __forceinline__ void boundary_epilogue(const PushParams &q, const DevGrid &g,
                                                   long long i, double &x, double y,
                                                   double &vx) {
-  if (q.flags & SKB_EPI_SHEAR) {
+  const int flags = (FLAGS >= 0) ? FLAGS : q.flags;
+  if (flags & SKB_EPI_SHEAR) {
     if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
     if (y >= (double)g.ny) { x = x + q.x_boost; vx = vx + q.vx_boost; }
   }
-  if (q.flags & SKB_EPI_HOLES) {
+  if (flags & SKB_EPI_HOLES) {
     if (y < g.e0 || y >= g.e1) {
       int slot = atomicAdd(q.ihole, 1);
       if (slot < q.ntmax) q.ihole[slot + 1] = (int)i + 1;
     }
   }
-  if (q.flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, (double)g.nx);
+  if (flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, (double)g.nx);
 }
 
 // gather + kick + drift + boundary epilogue for one particle
-template <int ORDER, bool MODIFIED>
+template <int ORDER, bool MODIFIED, int FLAGS = -1>
 __device__ __forceinline__ void push_one(const double *sE, const double *sB, const Window &w,
                                          int wstride, const double *E, const double *B,
                                          const DevGrid &g, const PushParams &q, long long i,
@@ -96,12 +100,13 @@ __device__ __forceinline__ void push_one(const double *sE, const double *sB, con
   // drift_particle, particle_push.pxd:88-91
   x = x + vx * q.dtdsx;
   y = y + vy * q.dtdsy;
-  if (q.flags) boundary_epilogue(q, g, i, x, y, vx);
+  if (FLAGS >= 0) { if (FLAGS) boundary_epilogue<FLAGS>(q, g, i, x, y, vx); }
+  else if (q.flags) boundary_epilogue<-1>(q, g, i, x, y, vx);
 }
 
 // resident CTAs per SM the register allocation aims for: 3 for CIC (80 registers, no
 // spills), 2 for TSC (118); measured best on B200
-template <int ORDER, bool MODIFIED>
+template <int ORDER, bool MODIFIED, int FLAGS>
 __global__ void __launch_bounds__(PUSH_THREADS, (ORDER == 1) ? 3 : 2)
 push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
             const double *__restrict__ B, DevGrid g, DevTiling tl, PushParams q,
@@ -110,6 +115,7 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
   double *sE = smem;
   double *sB = smem + (size_t)wstride * wrows * 3;
   double *pbuf = sB + (size_t)wstride * wrows * 3;   // [2][5][PUSH_THREADS] particle ring
+  const int flags = (FLAGS >= 0) ? FLAGS : q.flags;
 
   SegmentIter it;
   it.init(tl, np, span);
@@ -150,11 +156,11 @@ push_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
         const double *pb = pbuf + buf * 5 * PUSH_THREADS + threadIdx.x;
         double x = pb[0], y = pb[PUSH_THREADS], vx = pb[2 * PUSH_THREADS],
                vy = pb[3 * PUSH_THREADS], vz = pb[4 * PUSH_THREADS];
-        push_one<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
+        push_one<ORDER, MODIFIED, FLAGS>(sE, sB, w, wstride, E, B, g, q, i, x, y, vx, vy, vz);
         P.x[i] = x; P.y[i] = y; P.vx[i] = vx; P.vy[i] = vy; P.vz[i] = vz;
-        if ((q.flags & SKB_EPI_COUNT) && !(y < g.e0 || y >= g.e1)) key = cell_key(x, y, q.key);
+        if ((flags & SKB_EPI_COUNT) && !(y < g.e0 || y >= g.e1)) key = cell_key(x, y, q.key);
       }
-      if (q.flags & SKB_EPI_COUNT) {
+      if (flags & SKB_EPI_COUNT) {
         // first pass of the tile sort: one integer atomic per distinct new cell
         const unsigned peers = __match_any_sync(SKB_FULL, key);
         if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(q.cell_counts + key, __popc(peers));
@@ -259,6 +265,31 @@ push_sort_kernel(skb_particles_t P, long long np, const double *__restrict__ E,
   }
 }
 
+typedef void (*PushKernel)(skb_particles_t, long long, const double *, const double *,
+                           DevGrid, DevTiling, PushParams, int, int, int);
+
+template <int FLAGS>
+static PushKernel push_kernel_for(int order, bool modified) {
+  if (order == 1) return modified ? push_kernel<1, true, FLAGS> : push_kernel<1, false, FLAGS>;
+  return modified ? push_kernel<2, true, FLAGS> : push_kernel<2, false, FLAGS>;
+}
+
+// kernel instances with compile-time epilogue flags for the combinations Particles.push
+// uses (holes + x wrap [+ shear] [+ sort histogram]) and for "no epilogue"; anything
+// else runs the generic instance that reads the flags at run time
+static PushKernel select_push_kernel(int order, bool modified, int flags) {
+  const int HP = SKB_EPI_HOLES | SKB_EPI_PERIODIC_X;
+  switch (flags) {
+    case 0: return push_kernel_for<0>(order, modified);
+    case HP: return push_kernel_for<HP>(order, modified);
+    case HP | SKB_EPI_SHEAR: return push_kernel_for<HP | SKB_EPI_SHEAR>(order, modified);
+    case HP | SKB_EPI_COUNT: return push_kernel_for<HP | SKB_EPI_COUNT>(order, modified);
+    case HP | SKB_EPI_SHEAR | SKB_EPI_COUNT:
+      return push_kernel_for<HP | SKB_EPI_SHEAR | SKB_EPI_COUNT>(order, modified);
+    default: return push_kernel_for<-1>(order, modified);
+  }
+}
+
 // ihole[0] holds the raw count after the kernel; give it the reference's in-band
 // overflow encoding (particle_boundary.pxd:17-20: -ih of the last overflowing
 // particle, i.e. -(count-1))
@@ -323,11 +354,8 @@ extern "C" int skb_boris_push(skb_particles_t p, long long np, const double *E,
     const int ws = window_stride(tl), wr = window_rows(tl);
     size_t smem = ((size_t)ws * wr * 3 * 2 + 2 * 5 * PUSH_THREADS) * sizeof(double);
     long long nblk = (np + span - 1) / span;
-    void (*k)(skb_particles_t, long long, const double *, const double *, DevGrid,
-              DevTiling, PushParams, int, int, int);
-    if (order == 1) k = modified ? push_kernel<1, true> : push_kernel<1, false>;
-    else if (order == 2) k = modified ? push_kernel<2, true> : push_kernel<2, false>;
-    else return (int)cudaErrorInvalidValue;
+    if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
+    PushKernel k = select_push_kernel(order, modified != 0, q.flags);
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;

@@ -353,7 +353,7 @@ __device__ __forceinline__ void emit_one(double val, int idx, bool in_window, in
 // kernel (gather_cellsums_kernel) adds them into the source grid in a fixed order, so
 // the result depends only on the (canonically ordered) particle array.
 template <int ORDER, bool DET>
-__global__ void __launch_bounds__(DEP_THREADS)
+__global__ void __launch_bounds__(DEP_THREADS, 2)   // 2 CTAs/SM: at most 128 registers
 deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
                      DepParams q, int parts, int wstride, int wrows,
                      double *__restrict__ cellsums) {

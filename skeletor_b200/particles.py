@@ -349,6 +349,7 @@ class Particles:
         if self._mig is not None:
             return self._exchange_peer(nl, nr)
         for it in range(2000):
+            self.info[4] = max(self.info[4], it + 1)     # passes, pplib2.c:955
             if comm.size == 1:
                 # nvp == 1: rbufl = sbufr, rbufr = sbufl (pplib2.c:715-730)
                 from_below, from_above = self.sbufr[:nr], self.sbufl[:nl]
@@ -394,6 +395,7 @@ class Particles:
         arena = self._mig
         nkeep = 0
         for it in range(2000):
+            self.info[4] = max(self.info[4], it + 1)     # passes, pplib2.c:955
             self._sbl[0, :1].fill_(float(nl))
             self._sbr[0, :1].fill_(float(nr))
             from_below, from_above = arena.exchange(self._sbr[:nr + 1], self._sbl[:nl + 1])

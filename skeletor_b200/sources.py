@@ -62,6 +62,45 @@ class Sources(Field):
         self.add_guards()
         self.copy_guards()
 
+    def __iadd__(self, other):
+        """+= over all components (sources.py:72-89)"""
+        self.t.add_(other.t)
+        return self
+
+    def add_guards_x(self):
+        """Add the x guard cells to the corresponding active cells, all rows
+        (sources.py:91-101)"""
+        _lib.call("skb_add_guards", self.ptr, self.nc, self.grid.c, 0, None, None,
+                  _stream())
+
+    def add_guards_y(self):
+        """Add the y guard rows to the corresponding active rows, active x only; the
+        guards are NOT zeroed (sources.py:103-115)"""
+        g = self.grid
+        t = self.t
+        ax = slice(g.lbx, g.ubx)
+        up = t[g.uby:, ax].contiguous()       # my upper guards: for the rank above
+        dn = t[:g.lby, ax].contiguous()       # my lower guards: for the rank below
+        if g.comm.size > 1:
+            from_below, from_above = self._halo_exchange(up, dn)
+        else:
+            from_below, from_above = up, dn
+        t[g.uby:, ax] = from_below
+        t[:g.lby, ax] = from_above
+        for iy in range(g.lby):
+            t[iy + g.nyp, ax] += t[iy, ax]
+        for iy in range(g.uby + g.lby - 1, g.uby - 1, -1):
+            t[iy - g.nyp, ax] += t[iy, ax]
+
+    def add_guards_old(self):
+        """reference test helper (sources.py:152-192): same result as add_guards when
+        there is no shear"""
+        shear, self.shear = self.shear, False
+        try:
+            self.add_guards()
+        finally:
+            self.shear = shear
+
     def add_guards(self):
         "Add data from guard cells to corresponding active cells (sources.py:117-150)."
         g = self.grid

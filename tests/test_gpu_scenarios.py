@@ -148,3 +148,36 @@ print("compat OK")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True,
                        env=env, timeout=300)
     assert r.returncode == 0 and "compat OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_piecewise_guard_api_equals_fused():
+    """the reference's piecewise guard methods (copy_guards_x/_y, add_guards_x/_y, the
+    *_old test helpers; field.py:73-151, sources.py:91-192) give the fused results —
+    the bitwise new-vs-old check of reference tests/test_deposit.py:77,89"""
+    import skeletor_b200 as sk
+    m = sk.Manifold(32, 16, sk.COMM_SELF, lbx=1, lby=2)
+    rng = np.random.default_rng(8)
+    vals = {d: rng.uniform(-1, 1, (m.myp, m.mx)) for d in 'txyz'}
+
+    def fresh():
+        s = sk.Sources(m)
+        for d in 'txyz':
+            s[d][...] = vals[d]
+        return s
+    a, b, c = fresh(), fresh(), fresh()
+    a.add_guards()
+    b.add_guards_old()
+    c.add_guards_x()
+    c.add_guards_y()
+    c[:m.lby, :] = 0.0
+    c[m.uby:, :] = 0.0
+    c[:, m.ubx:] = 0.0
+    c[:, :m.lbx] = 0.0
+    assert np.all(np.asarray(a) == np.asarray(b)) and np.all(np.asarray(a) == np.asarray(c))
+    a.copy_guards()
+    b.copy_guards_old()
+    c.copy_guards_y()
+    c.copy_guards_x()
+    assert np.all(np.asarray(a) == np.asarray(b)) and np.all(np.asarray(a) == np.asarray(c))
+    a += b
+    assert np.allclose(np.asarray(a['t']), 2*np.asarray(b['t']))

@@ -763,3 +763,55 @@ def test_sort_disabled_path_matches_oracle():
     assert np.array_equal(gu.sorted_rows(np.asarray(ions[:ions.N])),
                           gu.sorted_rows(parts[0][:N[0]]))
     assert rel(np.asarray(src), so) < 1e-12
+
+
+def test_parity_at_two_million_particles():
+    """one full step (push + boundary epilogue + migration + tile sort + deposit + guards)
+    on a 256 x 256 grid with 32 particles per cell against the oracle: particles bit-exact,
+    sources <= 1e-12, and the size-independent properties (charge, momentum) exact to
+    rounding"""
+    import skeletor_b200 as sk
+    nx = ny = 256
+    npc = 32
+    g = orc.Grid(nx, ny, lbx=1, lby=1)
+    rng = np.random.default_rng(71)
+    n = nx*ny*npc
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    v = rng.normal(0, 0.3, (3, n))
+    E = random_field(g, orc.Float3, rng, -0.05, 0.05)
+    B = random_field(g, orc.Float3, rng)
+    dt = 0.3*g.dx
+    m = sk.Manifold(nx, ny, sk.COMM_SELF)
+    ions = sk.Particles(m, int(1.2*n), charge=0.7, mass=1.3)
+    ions.initialize(x, y, v[0], v[1], v[2])
+    Ef, Bf = sk.Field(m, dtype=sk.Float3), sk.Field(m, dtype=sk.Float3)
+    Ef[...] = E
+    Bf[...] = B
+    src = sk.Sources(m)
+    ions.push(Ef, Bf, dt)
+    src.deposit(ions)
+    raw = np.asarray(src).copy()
+    src.add_guards()
+    src.copy_guards()
+    p = np.zeros(int(1.2*n), orc.Particle)
+    p["x"][:n], p["y"][:n] = x/g.dx, y/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = v
+    orc.push(p[:n], E, B, g, 1, 0.7/1.3*dt/2, dt)
+    (q,), (nq,) = orc.move([p], [n], [g])
+    orc.periodic_x(q[:nq], g)
+    so = g.field(orc.Float4)
+    orc.deposit(q[:nq], so, g, 1)
+    orc.normalize([so], [g], [nq], 0.7, 1.0)
+    assert ions.N == nq == n
+    got = np.asarray(ions[:ions.N])
+    assert np.array_equal(gu.sorted_rows(got), gu.sorted_rows(q[:nq]))
+    assert rel(raw, so) < 1e-12
+    orc.add_guards([so], [g])
+    orc.copy_guards([so], [g])
+    assert rel(np.asarray(src), so) < 1e-12
+    # conservation: total charge and total current equal the particle sums
+    fac = 0.7*1.0*nx*ny/n
+    a = np.asarray(src)[1:-1, 1:-1]
+    assert abs(a['t'].sum() - fac*n) < 1e-9*fac*n
+    for c, name in (('x', 'vx'), ('y', 'vy'), ('z', 'vz')):
+        assert abs(a[c].sum() - fac*got[name].sum()) < 1e-9*fac*n

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--ny", type=int, default=NY)
     ap.add_argument("--ppc", type=int, default=PPC)
     ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--perturbed", action="store_true",
+                    help="5 %% sinusoidal density contrast along x (SURVEY.md 8d)")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: ny grows with the GPU count (ny rows PER GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -63,6 +65,7 @@ def workload_config(a, extra=None):
                        "push+deposit+add_guards+copy_guards per step" % (a.nx, a.ny, a.ppc),
            "grid": [a.nx, a.ny], "ppc": a.ppc, "particles": a.nx*a.ny*a.ppc,
            "interpolation": "CIC" if a.order == 1 else "TSC",
+           "plasma": "perturbed (5 % density contrast)" if a.perturbed else "uniform",
            "decomposition": "y-slabs, 1 per GPU", "vt_dt_over_dx": 0.1,
            "l2_policy": "inputs larger than L2 (>= 5 GB of particle data per GPU)"}
     if extra:
@@ -179,6 +182,11 @@ def b200_arm(a):
                                          dtype=torch.float64)*m.nyp
     d[2:5, :n_local] = torch.randn((3, n_local), generator=gen, device=dev,
                                    dtype=torch.float64)
+    if a.perturbed:
+        # displace x by (0.05 nx / 2 pi) sin(2 pi x / nx): ~5 % density contrast
+        xx = d[0, :n_local]
+        xx.add_(0.05*a.nx/(2*np.pi)*torch.sin(2*np.pi*xx/a.nx))
+        xx.remainder_(float(a.nx))
     ions.N = n_local
     dt = 0.1*m.dx       # vt = 1  ->  vt*dt/dx = 0.1
     E = sk.Field(m, dtype=sk.Float3)

@@ -64,6 +64,11 @@ typedef struct {
   int ntx, nty, tlx, tly;
   int chunk;                   /* particles per CTA work item */
   long long n_sorted;
+  /* gapped layout (skb_gap_*): cell k owns slots [gap_start[k], gap_start[k+1]) of the
+   * particle arrays and its gap_count[k] live particles sit at the front of that
+   * range.  NULL = dense layout (cell_end). */
+  const int *gap_start;
+  const int *gap_count;
 } skb_tiling_t;
 
 /* flags for the fused particle-boundary epilogue of skb_boris_push/skb_drift */
@@ -248,6 +253,48 @@ int skb_tile_sort_precounted(skb_particles_t in, skb_particles_t out, long long 
  * np.lexsort((vz, vy, vx, y, x, key)) of the same particles. */
 int skb_canonical_cells(skb_particles_t in, skb_particles_t out, const int *cell_end,
                         const skb_grid_t *grid, int tlx, int tly, void *stream);
+
+/* ---- gapped particle layout (new component): ordering without a move pass ---------
+ * Every cell owns a slot range with slack; gap_start [ncells+1] (slot ranges),
+ * gap_count [ncells] (live particles at the front of each range).
+ * skb_gap_build:   dense exactly-ordered arrays (cell_end) -> gapped arrays; nothing is
+ *   written when the slot ranges need more than `capacity` slots (gap_start[ncells]).
+ * skb_push_gapped: push (+ shear boost / x wrap: epi_flags, epi_S, epi_t) of every cell's
+ *   particles; stayers are written back compacted into their own range, particles that
+ *   change cell go to `movers` (AoS rows; counts[0]), particles that leave the slab to
+ *   sbufl / sbufr as skb_move_pack would (counts[1], counts[2]); counts[3] = flags
+ *   (1: mover list full, some particles were parked in their old cell -> rebuild;
+ *    2: exchange buffer overflow).
+ *   The nleft particles of `leftover` (below) are pushed first, with the generic
+ *   kernel, and join the head of the mover list (nleft <= mover_cap).
+ * skb_gap_insert:  drop AoS rows (movers, arrivals) into the free slots of their cells;
+ *   rows that do not fit go to `leftover`, a small SoA list [5][leftover_cap]
+ *   (counts[0] rows; counts[1] = leftover overflow) that lives beside the cells until
+ *   the next push.
+ * skb_gap_densify: gapped -> dense ordered arrays + cell_end + tile_offsets, leftover
+ *   rows appended behind the n_in_cells ordered particles.
+ * skb_exclusive_scan / skb_chunk_table: helpers shared with the tile sort. */
+int skb_gap_build(skb_particles_t in, skb_particles_t out, const int *cell_end,
+                  const skb_grid_t *grid, int tlx, int tly, int *gap_start,
+                  int *gap_count, int *block_sums, long long capacity, void *stream);
+int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
+                    const skb_grid_t *grid, int order, double qtmh, double dt,
+                    int modified, double Omega, double S, int epi_flags, double epi_S,
+                    double epi_t, int tlx, int tly, const int *gap_start, int *gap_count,
+                    double *movers, int mover_cap, double *sbufl, double *sbufr,
+                    int nbmax, int *counts, int rank, int nvp, double *leftover,
+                    int leftover_cap, int nleft, void *stream);
+int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
+                   int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
+                   double *leftover, int leftover_cap, int *counts, void *stream);
+int skb_gap_densify(skb_particles_t in, skb_particles_t out, const int *gap_start,
+                    const int *gap_count, const skb_grid_t *grid, int tlx, int tly,
+                    int *dense_start, int *cell_end, int *tile_offsets, int *block_sums,
+                    const double *leftover, int leftover_cap, int nleft,
+                    long long n_in_cells, void *stream);
+int skb_exclusive_scan(int *a, int n, int *block_sums, void *stream);
+int skb_chunk_table(const int *tile_offsets, const skb_grid_t *grid, int tlx, int tly,
+                    int chunk, int *chunk_first_tile, void *stream);
 
 /* ---- guard cells (NumPy slicing in the reference) ----------------------------
  * nc = doubles per cell (1, 3 or 4).

@@ -29,7 +29,8 @@ class ParticlesT(C.Structure):
 class TilingT(C.Structure):
     _fields_ = [("tile_offsets", c_vp), ("chunk_first_tile", c_vp),
                 ("cell_end", c_vp), ("ntx", c_int), ("nty", c_int), ("tlx", c_int), ("tly", c_int),
-                ("chunk", c_int), ("n_sorted", c_ll)]
+                ("chunk", c_int), ("n_sorted", c_ll), ("gap_start", c_vp),
+                ("gap_count", c_vp)]
 
 
 class EpilogueT(C.Structure):
@@ -77,6 +78,16 @@ SIGNATURES = {
     "skb_tile_sort_precounted": [_P, _P, c_ll, _G, c_int, c_int, c_int, c_int, c_vp,
                                  c_vp, c_vp, c_vp, c_vp],
     "skb_canonical_cells": [_P, _P, c_vp, _G, c_int, c_int, c_vp],
+    "skb_gap_build": [_P, _P, c_vp, _G, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_vp],
+    "skb_push_gapped": [_P, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_int, c_dbl, c_dbl,
+                        c_int, c_dbl, c_dbl, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp,
+                        c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
+    "skb_gap_insert": [c_vp, c_int, _P, c_vp, c_vp, _G, c_int, c_int, c_int, c_vp, c_int,
+                       c_vp, c_vp],
+    "skb_gap_densify": [_P, _P, c_vp, c_vp, _G, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                        c_vp, c_int, c_int, c_ll, c_vp],
+    "skb_exclusive_scan": [c_vp, c_int, c_vp, c_vp],
+    "skb_chunk_table": [c_vp, _G, c_int, c_int, c_int, c_vp, c_vp],
     "skb_copy_guards": [c_vp, c_int, _G, c_vp, c_vp, c_vp],
     "skb_add_guards": [c_vp, c_int, _G, c_int, c_vp, c_vp, c_vp],
     "skb_pack_rows": [c_vp, c_int, _G, c_int, c_int, c_vp, c_vp],
@@ -101,7 +112,8 @@ kernel_launches = 0   # CUDA kernels those calls launched (bench.py's gpu_launch
 
 # kernels launched per C-ABI call (memsets are not counted)
 KERNELS_PER_CALL = {"skb_tile_sort": 6, "skb_calculate_ihole": 3, "skb_move_unpack": 3,
-                    "skb_sort_scan": 4, "skb_sort_clear": 0, "skb_tile_sort_precounted": 5, "skb_deposit_deterministic": 2}
+                    "skb_sort_scan": 4, "skb_sort_clear": 0, "skb_tile_sort_precounted": 5, "skb_deposit_deterministic": 2,
+                    "skb_gap_build": 5, "skb_gap_densify": 5, "skb_exclusive_scan": 3}
 
 
 class SkeletorCudaError(RuntimeError):

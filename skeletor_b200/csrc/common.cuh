@@ -38,19 +38,22 @@ struct DevTiling {
   const int *tile_offsets;
   const int *chunk_first_tile;
   const int *cell_end;
+  const int *gap_start, *gap_count;
   int ntx, nty, tlx, tly, chunk;
   long long n_sorted;
 };
 
 static inline DevTiling make_tiling(const skb_tiling_t *t) {
   DevTiling d;
-  if (t && t->tile_offsets) {
+  if (t && (t->tile_offsets || t->gap_start)) {
     d.tile_offsets = t->tile_offsets; d.chunk_first_tile = t->chunk_first_tile;
     d.cell_end = t->cell_end;
+    d.gap_start = t->gap_start; d.gap_count = t->gap_count;
     d.ntx = t->ntx; d.nty = t->nty; d.tlx = t->tlx; d.tly = t->tly;
     d.chunk = t->chunk; d.n_sorted = t->n_sorted;
   } else {
     d.tile_offsets = nullptr; d.chunk_first_tile = nullptr; d.cell_end = nullptr;
+    d.gap_start = nullptr; d.gap_count = nullptr;
     d.ntx = d.nty = 1; d.tlx = d.tly = 4; d.chunk = 2048; d.n_sorted = 0;
   }
   return d;

@@ -365,8 +365,11 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
   const int cpp = (1 << cells_log2) / parts;          // cells per CTA
   const int tile = blockIdx.x / parts;
   const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
-  const int pbeg = c0 ? tl.cell_end[c0 - 1] : 0;
-  const int pend = tl.cell_end[c0 + cpp - 1];
+  // dense layout: cell k = [cell_end[k-1], cell_end[k]); gapped layout: cell k =
+  // [gap_start[k], gap_start[k] + gap_count[k])
+  const bool gapped = tl.gap_start != nullptr;
+  const int pbeg = gapped ? tl.gap_start[c0] : (c0 ? tl.cell_end[c0 - 1] : 0);
+  const int pend = gapped ? tl.gap_start[c0 + cpp] : tl.cell_end[c0 + cpp - 1];
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   if (pbeg == pend) {                                  // uniform: no particles here
     if (DET)
@@ -385,18 +388,27 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
   const int wc0 = c0 + wv * cpw;
   for (int cb = 0; cb < cpw; cb += 32) {
     const int mycell = wc0 + cb + lane;
-    const int my_end = (cb + lane < cpw) ? tl.cell_end[mycell] : 0;
-    int prev_end = (wc0 + cb) ? tl.cell_end[wc0 + cb - 1] : 0;
+    const bool mine = cb + lane < cpw;
+    const int my_end = mine ? (gapped ? tl.gap_count[mycell] : tl.cell_end[mycell]) : 0;
+    const int my_start = (mine && gapped) ? tl.gap_start[mycell] : 0;
+    int prev_end = gapped ? 0 : ((wc0 + cb) ? tl.cell_end[wc0 + cb - 1] : 0);
     const int ncell = min(32, cpw - cb);
     for (int j = 0; j < ncell; j++) {
-      const int s = prev_end;
-      const int e = __shfl_sync(SKB_FULL, my_end, j);
+      int s = prev_end;
+      int e = __shfl_sync(SKB_FULL, my_end, j);
+      int next = e;                                    // where the following particles start
+      if (gapped) {
+        s = __shfl_sync(SKB_FULL, my_start, j);
+        e += s;
+        next = __shfl_sync(SKB_FULL, my_start, min(j + 1, 31));
+        if (j + 1 >= ncell) next = pend;
+      }
       prev_end = e;
       {
         // pull the particles that follow this cell (the warp's next cells) into L2
         // while this one is being reduced: 128-byte lines, one per lane and array
-        const int ahead = e + lane * 16;
-        if (ahead < min(e + 16 * DEP_PREFETCH_LINES, pend)) {
+        const int ahead = next + lane * 16;
+        if (ahead < min(next + 16 * DEP_PREFETCH_LINES, pend)) {
           dep_prefetch_l2(P.x + ahead); dep_prefetch_l2(P.y + ahead);
           dep_prefetch_l2(P.vx + ahead); dep_prefetch_l2(P.vy + ahead);
           dep_prefetch_l2(P.vz + ahead);
@@ -724,8 +736,8 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
   q.S = S;
   FusedParams fq = {};
   if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
-  if (tl.tile_offsets && tl.cell_end && tl.n_sorted > 0) {
-    // exact ordering with per-cell ranges: whole cells per warp
+  if ((tl.gap_start && tl.gap_count) || (tl.tile_offsets && tl.cell_end && tl.n_sorted > 0)) {
+    // exact ordering with per-cell ranges (dense or gapped): whole cells per warp
     const int ntiles = tl.ntx * tl.nty;
     const int cells = 1 << (tl.tlx + tl.tly);
     int parts = 1;
@@ -733,7 +745,7 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
     const int ws = window_stride(tl), wr = window_rows(tl);
     const size_t smem = (size_t)ws * wr * 4 * sizeof(double);
     if (cellsums) {
-      if (np != tl.n_sorted) return (int)cudaErrorInvalidValue;  // needs a full exact order
+      if (tl.gap_start || np != tl.n_sorted) return (int)cudaErrorInvalidValue;  // needs a full exact dense order
       if (order == 1)
         deposit_cells_kernel<1, true><<<ntiles * parts, DEP_THREADS, 0, st>>>(p, current, g, tl, q, parts, ws, wr, cellsums);
       else
@@ -751,7 +763,7 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
     else
       deposit_cells_kernel<2, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);
     SKB_CHECK_LAUNCH();
-    if (np <= tl.n_sorted) return 0;
+    if (tl.gap_start || np <= tl.n_sorted) return 0;
     // unsorted tail [n_sorted, np): generic kernel without ordering
     const long long n0 = tl.n_sorted;
     p.x += n0; p.y += n0; p.vx += n0; p.vy += n0; p.vz += n0;

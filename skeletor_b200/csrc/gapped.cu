@@ -1,0 +1,446 @@
+// gapped.cu — gapped particle layout: sort maintenance without moving every particle.
+//
+// The tile sort's move pass costs 80 B/particle per step although only ~15 % of the
+// particles change cell.  In the gapped layout every cell owns a slot range with some
+// slack ([gap_start[k], gap_start[k+1]), live particles at the front, gap_count[k] of
+// them).  The push then
+//   * writes the particles that stay in their cell back into the same range, compacted
+//     to the front (it has to write them anyway: 80 B/particle, as before),
+//   * appends the few that change cell to a mover list (AoS rows) and the ones that
+//     leave the slab to the exchange buffers (cppmove2's pack, pplib2.c:666-707),
+// and a small insertion kernel drops movers and arrivals into the free slots of their
+// new cells.  No histogram, no scan, no move pass: ~100 B/particle for push + ordering
+// instead of 160 B.  When a cell's slack or the mover list overflows, nothing is lost:
+// the particle stays where it is (or in the leftover list), a flag is raised and the
+// caller rebuilds the layout through the dense path (densify -> tile sort -> build).
+//
+// New component (no reference counterpart); ordering stays a performance property.
+#include "common.cuh"
+#include "gather.cuh"
+
+#define GAP_THREADS 256
+#define GAP_UNR 2
+
+__device__ __forceinline__ void gap_prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// ---- build / densify ----------------------------------------------------------------
+// capacity of a cell with n particles: n + max(16, n/4), rounded up to 16 slots (128 B)
+__global__ void __launch_bounds__(256)
+gap_caps_kernel(const int *__restrict__ cell_end, int ncells, int *gap_start) {
+  int c = blockIdx.x * 256 + threadIdx.x;
+  if (c > ncells) return;
+  if (c == ncells) { gap_start[c] = 0; return; }
+  const int n = cell_end[c] - (c ? cell_end[c - 1] : 0);
+  gap_start[c] = (n + max(16, n >> 2) + 15) & ~15;
+}
+
+// dense (cell_end) -> gapped (gap_start already scanned); one warp per cell
+__global__ void __launch_bounds__(256)
+gap_fill_kernel(skb_particles_t in, skb_particles_t out, const int *__restrict__ cell_end,
+                const int *__restrict__ gap_start, int *gap_count, int ncells,
+                long long capacity) {
+  // slot ranges do not fit the arrays: write nothing (the host reads gap_start[ncells])
+  if (gap_start[ncells] > capacity || gap_start[ncells] < 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * 256) >> 5;
+  for (int c = (blockIdx.x * 256 + threadIdx.x) >> 5; c < ncells; c += warps) {
+    const int s = c ? cell_end[c - 1] : 0, n = cell_end[c] - s, d = gap_start[c];
+    for (int i = lane; i < n; i += 32) {
+      out.x[d + i] = in.x[s + i]; out.y[d + i] = in.y[s + i]; out.vx[d + i] = in.vx[s + i];
+      out.vy[d + i] = in.vy[s + i]; out.vz[d + i] = in.vz[s + i];
+    }
+    if (lane == 0) gap_count[c] = n;
+  }
+}
+
+// gapped -> dense: dense_start = exclusive scan of gap_count (array of ncells + 1 ints);
+// writes cell_end and the tile offsets of the dense ordering
+__global__ void __launch_bounds__(256)
+gap_densify_kernel(skb_particles_t in, skb_particles_t out, const int *__restrict__ gap_start,
+                   const int *__restrict__ gap_count, const int *__restrict__ dense_start,
+                   int *cell_end, int *tile_offsets, int ncells, int cells_log2) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * 256) >> 5;
+  for (int c = (blockIdx.x * 256 + threadIdx.x) >> 5; c < ncells; c += warps) {
+    const int s = gap_start[c], n = gap_count[c], d = dense_start[c];
+    for (int i = lane; i < n; i += 32) {
+      out.x[d + i] = in.x[s + i]; out.y[d + i] = in.y[s + i]; out.vx[d + i] = in.vx[s + i];
+      out.vy[d + i] = in.vy[s + i]; out.vz[d + i] = in.vz[s + i];
+    }
+    if (lane == 0) {
+      cell_end[c] = d + n;
+      if ((c & ((1 << cells_log2) - 1)) == 0) tile_offsets[c >> cells_log2] = d;
+      if (c == ncells - 1) tile_offsets[ncells >> cells_log2] = d + n;
+    }
+  }
+}
+
+// leftover list (SoA, stride cap) -> tail of the dense arrays
+__global__ void __launch_bounds__(256)
+gap_append_rows_kernel(const double *__restrict__ lo, int cap, int n, skb_particles_t out,
+                       long long at) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  out.x[at + i] = lo[i]; out.y[at + i] = lo[(size_t)cap + i];
+  out.vx[at + i] = lo[2 * (size_t)cap + i]; out.vy[at + i] = lo[3 * (size_t)cap + i];
+  out.vz[at + i] = lo[4 * (size_t)cap + i];
+}
+
+// pushed leftover particles (SoA) -> exchange buffers or the head of the mover list
+__global__ void __launch_bounds__(256)
+gap_route_kernel(const double *__restrict__ lo, int cap, int n, double e0, double e1,
+                 double ny, int rank, int nvp, double *movers, double *sbufl,
+                 double *sbufr, int nbmax, int *counts) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double x = lo[i], vx = lo[2 * (size_t)cap + i], vy = lo[3 * (size_t)cap + i],
+               vz = lo[4 * (size_t)cap + i];
+  double y = lo[(size_t)cap + i];
+  double *r;
+  if (y < e0 || y >= e1) {
+    int slot; double *buf;
+    if (y < e0) {
+      if (rank == 0) y += ny;
+      slot = atomicAdd(counts + 1, 1); buf = sbufl;
+    } else {
+      if (rank == nvp - 1) y -= ny;
+      slot = atomicAdd(counts + 2, 1); buf = sbufr;
+    }
+    if (slot >= nbmax) { atomicOr(counts + 3, 2); return; }
+    r = buf + (size_t)slot * 5;
+  } else {
+    r = movers + (size_t)atomicAdd(counts + 0, 1) * 5;   // n <= mover_cap: always fits
+  }
+  r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+}
+
+// ---- insertion of movers / arrivals ---------------------------------------------------
+// rows whose x carries this bit pattern are padding of the mover list (unused tail of a
+// warp's slot reservation) and are skipped
+#define GAP_PAD_BITS 0x7ff8dead0badf00dLL
+#define GAP_MCHUNK 64
+
+// One slot claim per warp and destination cell (rows arrive roughly ordered by source
+// tile, so a warp sees few distinct cells and its writes into one cell are contiguous).
+__global__ void __launch_bounds__(256)
+gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
+                  const int *__restrict__ gap_start, int *gap_count, KeyParams kp,
+                  double *leftover, int leftover_cap, int *counts) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+  bool valid = i < n;
+  if (valid) {
+    const double *r = rows + (size_t)i * 5;
+    r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3]; r4 = r[4];
+    valid = __double_as_longlong(r0) != GAP_PAD_BITS;
+  }
+  const int key = valid ? cell_key(r0, r1, kp) : -1 - lane;
+  const unsigned peers = __match_any_sync(SKB_FULL, key);
+  const int leader = __ffs(peers) - 1, rank = __popc(peers & lt), cnt = __popc(peers);
+  int s = 0, cap = 0, base = 0;
+  if (valid && lane == leader) {
+    s = gap_start[key]; cap = gap_start[key + 1] - s;
+    base = atomicAdd(gap_count + key, cnt);
+    const int over = min(max(base + cnt - cap, 0), cnt);
+    if (over) atomicSub(gap_count + key, over);  // cell full: those go to the leftovers
+  }
+  s = __shfl_sync(SKB_FULL, s, leader);
+  cap = __shfl_sync(SKB_FULL, cap, leader);
+  base = __shfl_sync(SKB_FULL, base, leader);
+  if (!valid) return;
+  const int slot = base + rank;
+  if (slot < cap) {
+    const long long d = (long long)s + slot;
+    P.x[d] = r0; P.y[d] = r1; P.vx[d] = r2; P.vy[d] = r3; P.vz[d] = r4;
+  } else {
+    const int l = atomicAdd(counts + 0, 1);
+    if (l < leftover_cap) {
+      const size_t lc = (size_t)leftover_cap;
+      leftover[l] = r0; leftover[lc + l] = r1; leftover[2 * lc + l] = r2;
+      leftover[3 * lc + l] = r3; leftover[4 * lc + l] = r4;
+    } else {
+      counts[1] = 1;                            // even the leftover list is full
+    }
+  }
+}
+
+// ---- push on the gapped layout -----------------------------------------------------------
+struct GapPush {
+  KickParams k;
+  double dtdsx, dtdsy, vx_boost, x_boost;
+  int flags;                 // SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X
+  KeyParams key;
+  int *gap_count;            // updated in place
+  double *movers;            // AoS rows
+  int mover_cap;
+  double *sbufl, *sbufr;
+  int nbmax, rank, nvp;
+  int *counts;               // [0] movers, [1] sbufl, [2] sbufr, [3] flags (1: mover list
+                             // full -> some particles sit in the wrong cell, 2: nbmax)
+};
+
+template <int ORDER, bool MODIFIED>
+__global__ void __launch_bounds__(GAP_THREADS, 2)
+push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
+                   const double *__restrict__ B, DevGrid g, DevTiling tl, GapPush q,
+                   int parts, int wstride, int wrows) {
+  extern __shared__ double smem[];
+  double *sE = smem;
+  double *sB = smem + (size_t)wstride * wrows * 3;
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const int pend = tl.gap_start[c0 + cpp];
+  const Window w = tile_window(tile, tl, g);
+  stage_window(sE, E, w, wstride, g);
+  stage_window(sB, B, w, wstride, g);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int cpw = cpp / (GAP_THREADS / 32);
+  const int wc0 = c0 + wv * cpw;
+  const double nxd = (double)g.nx;
+  // mover slots are reserved GAP_MCHUNK at a time per warp (one global atomic per chunk
+  // instead of one per 32 particles on a single address)
+  int mbase = 0, mused = GAP_MCHUNK;
+  for (int cb = 0; cb < cpw; cb += 32) {
+    const bool mine = cb + lane < cpw;
+    const int my_cnt = mine ? q.gap_count[wc0 + cb + lane] : 0;
+    const int my_start = mine ? tl.gap_start[wc0 + cb + lane] : 0;
+    const int ncell = min(32, cpw - cb);
+    for (int j = 0; j < ncell; j++) {
+      const int cell = wc0 + cb + j;
+      const int s = __shfl_sync(SKB_FULL, my_start, j);
+      const int n = __shfl_sync(SKB_FULL, my_cnt, j);
+      {
+        int next = __shfl_sync(SKB_FULL, my_start, min(j + 1, 31));
+        if (j + 1 >= ncell) next = pend;
+        const int ahead = next + lane * 16;
+        if (ahead < min(next + 16 * 16, pend)) {
+          gap_prefetch_l2(P.x + ahead); gap_prefetch_l2(P.y + ahead);
+          gap_prefetch_l2(P.vx + ahead); gap_prefetch_l2(P.vy + ahead);
+          gap_prefetch_l2(P.vz + ahead);
+        }
+      }
+      if (n == 0) continue;
+      int wcur = 0;                                  // stayers written so far
+      for (int base = 0; base < n; base += 32 * GAP_UNR) {
+        double x[GAP_UNR], y[GAP_UNR], vx[GAP_UNR], vy[GAP_UNR], vz[GAP_UNR];
+#pragma unroll
+        for (int u = 0; u < GAP_UNR; u++) {
+          const int i = base + u * 32 + lane;
+          if (i < n) {
+            x[u] = P.x[s + i]; y[u] = P.y[s + i]; vx[u] = P.vx[s + i];
+            vy[u] = P.vy[s + i]; vz[u] = P.vz[s + i];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < GAP_UNR; u++) {
+          const int i = base + u * 32 + lane;
+          const bool act = i < n;
+          bool stay = false, mover = false;
+          if (act) {
+            fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x[u], y[u],
+                                             vx[u], vy[u], vz[u]);
+            x[u] = x[u] + vx[u] * q.dtdsx;          // drift_particle, particle_push.pxd:88-91
+            y[u] = y[u] + vy[u] * q.dtdsy;
+            if (q.flags & SKB_EPI_SHEAR) {           // particle_boundary.pyx:41-49
+              if (y[u] < 0.0) { x[u] = x[u] - q.x_boost; vx[u] = vx[u] - q.vx_boost; }
+              if (y[u] >= (double)g.ny) { x[u] = x[u] + q.x_boost; vx[u] = vx[u] + q.vx_boost; }
+            }
+            if (q.flags & SKB_EPI_PERIODIC_X) x[u] = wrap_x(x[u], nxd);
+            if (y[u] < g.e0 || y[u] >= g.e1) {       // leaves the slab: cppmove2's pack
+              double *buf; int slot; double yy = y[u];
+              if (yy < g.e0) {
+                if (q.rank == 0) yy += (double)g.ny;
+                slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
+              } else {
+                if (q.rank == q.nvp - 1) yy -= (double)g.ny;
+                slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
+              }
+              if (slot < q.nbmax) {
+                double *r = buf + (size_t)slot * 5;
+                r[0] = x[u]; r[1] = yy; r[2] = vx[u]; r[3] = vy[u]; r[4] = vz[u];
+              } else {
+                atomicOr(q.counts + 3, 2);
+              }
+            } else {
+              stay = cell_key(x[u], y[u], q.key) == cell;
+              mover = !stay;
+            }
+          }
+          // movers: one slot claim per warp
+          const unsigned mm = __ballot_sync(SKB_FULL, mover);
+          if (mm) {
+            const int k = __popc(mm), room = GAP_MCHUNK - mused;
+            int nb = mbase;
+            if (k > room) {
+              if (lane == 0) nb = atomicAdd(q.counts + 0, GAP_MCHUNK);
+              nb = __shfl_sync(SKB_FULL, nb, 0);
+            }
+            if (mover) {
+              const int r = __popc(mm & lt);
+              const int slot = r < room ? mbase + mused + r : nb + (r - room);
+              if (slot < q.mover_cap) {
+                double *r = q.movers + (size_t)slot * 5;
+                r[0] = x[u]; r[1] = y[u]; r[2] = vx[u]; r[3] = vy[u]; r[4] = vz[u];
+              } else {
+                stay = true;                         // list full: park it here, rebuild later
+                atomicOr(q.counts + 3, 1);
+              }
+            }
+            if (k > room) { mbase = nb; mused = k - room; } else mused += k;
+          }
+          // stayers: compacted to the front of the cell's range
+          const unsigned sm = __ballot_sync(SKB_FULL, stay);
+          if (stay) {
+            const int d = s + wcur + __popc(sm & lt);
+            P.x[d] = x[u]; P.y[d] = y[u]; P.vx[d] = vx[u]; P.vy[d] = vy[u]; P.vz[d] = vz[u];
+          }
+          wcur += __popc(sm);
+        }
+      }
+      if (lane == 0) q.gap_count[cell] = wcur;
+    }
+  }
+  // unused tail of this warp's last reservation: padding rows
+  for (int r = mused + lane; r < GAP_MCHUNK; r += 32)
+    if (mbase + r < q.mover_cap)
+      q.movers[(size_t)(mbase + r) * 5] = __longlong_as_double(GAP_PAD_BITS);
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------
+extern "C" int skb_exclusive_scan(int *a, int n, int *block_sums, void *stream);
+extern "C" int skb_tile_geometry(const skb_grid_t *grid, int tlx, int tly, int *ntx, int *nty);
+
+static int gap_ncells(const skb_grid_t *grid, int tlx, int tly) {
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  return (ntx * nty) << (tlx + tly);
+}
+
+extern "C" int skb_gap_build(skb_particles_t in, skb_particles_t out, const int *cell_end,
+                             const skb_grid_t *grid, int tlx, int tly, int *gap_start,
+                             int *gap_count, int *block_sums, long long capacity,
+                             void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ncells = gap_ncells(grid, tlx, tly);
+  gap_caps_kernel<<<(ncells + 256) / 256, 256, 0, st>>>(cell_end, ncells, gap_start);
+  SKB_CHECK_LAUNCH();
+  int rc = skb_exclusive_scan(gap_start, ncells + 1, block_sums, stream);
+  if (rc) return rc;
+  int blocks = min((ncells + 7) / 8, 148 * 16);
+  gap_fill_kernel<<<blocks, 256, 0, st>>>(in, out, cell_end, gap_start, gap_count, ncells,
+                                          capacity);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_gap_densify(skb_particles_t in, skb_particles_t out, const int *gap_start,
+                               const int *gap_count, const skb_grid_t *grid, int tlx,
+                               int tly, int *dense_start, int *cell_end, int *tile_offsets,
+                               int *block_sums, const double *leftover, int leftover_cap,
+                               int nleft, long long n_in_cells, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ncells = gap_ncells(grid, tlx, tly);
+  cudaError_t e = cudaMemcpyAsync(dense_start, gap_count, sizeof(int) * (size_t)ncells,
+                                  cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(dense_start + ncells, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  int rc = skb_exclusive_scan(dense_start, ncells + 1, block_sums, stream);
+  if (rc) return rc;
+  int blocks = min((ncells + 7) / 8, 148 * 16);
+  gap_densify_kernel<<<blocks, 256, 0, st>>>(in, out, gap_start, gap_count, dense_start,
+                                             cell_end, tile_offsets, ncells, tlx + tly);
+  SKB_CHECK_LAUNCH();
+  if (nleft > 0) {
+    gap_append_rows_kernel<<<(nleft + 255) / 256, 256, 0, st>>>(leftover, leftover_cap,
+                                                                nleft, out, n_in_cells);
+    SKB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int skb_gap_insert(const double *rows, int n, skb_particles_t p,
+                              const int *gap_start, int *gap_count, const skb_grid_t *grid,
+                              int order, int tlx, int tly, double *leftover,
+                              int leftover_cap, int *counts, void *stream) {
+  if (n <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  gap_insert_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      rows, n, p, gap_start, gap_count, kp, leftover, leftover_cap, counts);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
+                               const skb_grid_t *grid, int order, double qtmh, double dt,
+                               int modified, double Omega, double S, int epi_flags,
+                               double epi_S, double epi_t, int tlx, int tly,
+                               const int *gap_start, int *gap_count, double *movers,
+                               int mover_cap, double *sbufl, double *sbufr, int nbmax,
+                               int *counts, int rank, int nvp, double *leftover,
+                               int leftover_cap, int nleft, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
+  DevGrid g = make_grid(grid);
+  skb_tiling_t t = {};
+  skb_tile_geometry(grid, tlx, tly, &t.ntx, &t.nty);
+  t.tlx = tlx; t.tly = tly; t.chunk = 2048;
+  t.gap_start = gap_start; t.gap_count = gap_count;
+  DevTiling tl = make_tiling(&t);
+  GapPush q;
+  q.k = make_kick(g, qtmh, dt, Omega, S);
+  q.dtdsx = dt / g.dx; q.dtdsy = dt / g.dy;
+  q.vx_boost = epi_S * g.Ly;                       // particle_boundary.pyx:37-38
+  q.x_boost = q.vx_boost * epi_t / g.dx;
+  q.flags = epi_flags;
+  q.key = make_keyparams(g, order, tlx, tly);
+  q.gap_count = gap_count; q.movers = movers; q.mover_cap = mover_cap;
+  q.sbufl = sbufl; q.sbufr = sbufr; q.nbmax = nbmax; q.rank = rank; q.nvp = nvp;
+  q.counts = counts;
+  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = t.ntx * t.nty;
+  const int cells = 1 << (tlx + tly);
+  int parts = 1;
+  while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
+  const int ws = window_stride(tl), wr = window_rows(tl);
+  const size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
+  void (*k)(skb_particles_t, const double *, const double *, DevGrid, DevTiling, GapPush,
+            int, int, int);
+  if (order == 1) k = modified ? push_gapped_kernel<1, true> : push_gapped_kernel<1, false>;
+  else k = modified ? push_gapped_kernel<2, true> : push_gapped_kernel<2, false>;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (nleft > 0) {
+    // the particles that found no slot last step: generic push in place, then onto the
+    // head of the mover list (or out to the neighbours) like everybody else
+    if (nleft > leftover_cap || nleft > mover_cap) return (int)cudaErrorInvalidValue;
+    const size_t lc = (size_t)leftover_cap;
+    skb_particles_t lp = {leftover, leftover + lc, leftover + 2 * lc, leftover + 3 * lc,
+                          leftover + 4 * lc};
+    skb_epilogue_t ep = {};
+    ep.flags = epi_flags & (SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X);
+    ep.S = epi_S; ep.t = epi_t;
+    int rc = skb_boris_push(lp, nleft, E, B, grid, order, qtmh, dt, modified, Omega, S,
+                            nullptr, &ep, stream);
+    if (rc) return rc;
+    gap_route_kernel<<<(nleft + 255) / 256, 256, 0, st>>>(
+        leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
+        sbufr, nbmax, counts);
+    SKB_CHECK_LAUNCH();
+  }
+  k<<<ntiles * parts, GAP_THREADS, smem, st>>>(p, E, B, g, tl, q, parts, ws, wr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}

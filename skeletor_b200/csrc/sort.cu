@@ -124,7 +124,7 @@ scan_apply_kernel(int *a, int n, const int *__restrict__ block_sums, int cells_l
     int excl = carry_s + woff + s - v;
     if (i < n) {
       a[i] = excl;
-      if ((i & ((1LL << cells_log2) - 1)) == 0) tile_offsets[i >> cells_log2] = excl;
+      if (tile_offsets && (i & ((1LL << cells_log2) - 1)) == 0) tile_offsets[i >> cells_log2] = excl;
     }
     __syncthreads();
     if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + v;
@@ -452,6 +452,33 @@ extern "C" int skb_canonical_cells(skb_particles_t in, skb_particles_t out,
   if (e != cudaSuccess) return (int)e;
   canonical_cells_kernel<<<blocks, SORT_THREADS, smem, (cudaStream_t)stream>>>(in, out,
                                                                              cell_end, ncells);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+// in-place exclusive scan of n ints (n <= 4096 * 4096); block_sums: >= 4100 ints
+extern "C" int skb_exclusive_scan(int *a, int n, int *block_sums, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb > 4096) return (int)cudaErrorInvalidValue;
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(a, n, block_sums);
+  SKB_CHECK_LAUNCH();
+  scan_top_kernel<<<1, 1024, 0, st>>>(block_sums, nb);
+  SKB_CHECK_LAUNCH();
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(a, n, block_sums, 30, nullptr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+// chunk -> first tile table for a given dense ordering (tile_offsets)
+extern "C" int skb_chunk_table(const int *tile_offsets, const skb_grid_t *grid, int tlx,
+                               int tly, int chunk, int *chunk_first_tile, void *stream) {
+  int ntx, nty;
+  skb_tile_geometry(grid, tlx, tly, &ntx, &nty);
+  const int ntiles = ntx * nty;
+  chunk_table_kernel<<<(ntiles + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      tile_offsets, ntiles, chunk, chunk_first_tile);
   SKB_CHECK_LAUNCH();
   return 0;
 }

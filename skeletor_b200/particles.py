@@ -38,6 +38,7 @@ class ParticleSlice:
         self.parent, self.sl = parent, sl
 
     def __array__(self, dtype=None, copy=None):
+        self.parent._dense()
         a = self.parent._data[:, self.sl].t().contiguous().cpu().numpy()
         out = np.zeros(a.shape[0], Particle)
         for k, r in _ROW.items():
@@ -148,6 +149,15 @@ class Particles:
         self.deterministic = False    # canonical intra-cell order after every sort
         self.fused_push = False   # two-pass recompute path: correct, but the push is
         # instruction-bound, so it is not faster than push + precounted sort
+        # gapped layout (see _push_gapped): particles stay ordered without a full move
+        # pass.  Needs Nmax >= ~1.3 N; push()/push_modified() fall back to the dense
+        # path when the slot ranges do not fit.
+        self.gapped = False
+        self.mover_fraction = 0.25    # size of the mover list relative to Nmax
+        self._rep = "dense"
+        self._gap_start = None
+        self._gap_nleft = 0
+        self._gap_dirty = False
 
     # -- particle counts ------------------------------------------------------------
     @property
@@ -188,6 +198,7 @@ class Particles:
         self._sorted = False
 
     def __getitem__(self, key):
+        self._dense()
         if isinstance(key, str):
             return DeviceArray(self._data[_ROW[key]], on_write=self._touched)
         if isinstance(key, slice):
@@ -205,6 +216,7 @@ class Particles:
             raise TypeError("unsupported particle assignment")
 
     def __array__(self, dtype=None, copy=None):
+        self._dense()
         return np.asarray(ParticleSlice(self, slice(None)))
 
     # -- C ABI views ---------------------------------------------------------------
@@ -219,6 +231,11 @@ class Particles:
         return self._soa(self._data)
 
     def _tiling_c(self):
+        if self._rep == "gapped":
+            # cell k = slots [gap_start[k], gap_start[k] + gap_count[k])
+            return C.pointer(_lib.TilingT(
+                None, None, None, self._ntx, self._nty, TLX, TLY, CHUNK, 0,
+                self._gap_start.data_ptr(), self._gap_count.data_ptr()))
         if not (self._sorted and self._n_sorted > 0):
             return None
         return C.pointer(_lib.TilingT(
@@ -237,6 +254,7 @@ class Particles:
         """Counting sort by tile-major stencil-base cell (skb_tile_sort).
         precounted: the key histogram is already in place (fused into the push
         epilogue + arrivals), so the 16 B/particle key pass is skipped."""
+        self._dense()
         if self.N == 0 or not self.sort_enabled:
             self._sorted = False
             return
@@ -272,13 +290,135 @@ class Particles:
         return self._cellsums_buf
 
     def _ensure_sorted(self):
+        if self._rep == "gapped":
+            return                  # ordered by construction
         if not self._sorted:
             self.sort()
+
+    # -- gapped layout ---------------------------------------------------------------
+    def _gap_alloc(self):
+        if self._gap_start is None:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            f64 = dict(dtype=torch.float64, device=self.device)
+            nc = self._cell_counts.numel()                    # ncells + 1
+            self._gap_start = torch.zeros(nc, **i32)
+            self._gap_count = torch.zeros(nc, **i32)
+            # every warp of skb_push_gapped reserves mover rows 64 at a time
+            ntiles = self._ntx*self._nty
+            warps = 8*max(ntiles, min(2368, 32*ntiles))
+            mcap = max(int(self.mover_fraction*self.size), 1024) + 64*warps
+            self._movers = torch.zeros((mcap, 5), **f64)
+            # particles whose cell ran out of slots: small unordered SoA list beside
+            # the cells, pushed / deposited by the generic kernels
+            self._leftover = torch.zeros((5, max(mcap//8, 1024)), **f64)
+            self._gcnt = torch.zeros(8, **i32)
+
+    def _to_gapped(self):
+        """dense ordered arrays -> per-cell slot ranges with slack (skb_gap_build).
+        Returns False (and stays dense) when the ranges do not fit in Nmax slots."""
+        if self.N == 0 or not self.sort_enabled or self.deterministic:
+            return False
+        if not (self._sorted and self._n_sorted == self.N):
+            self.sort()
+        self._gap_alloc()
+        _lib.call("skb_gap_build", self._c, self._soa(self._alt),
+                  self._cell_counts.data_ptr(), self.manifold.c, TLX, TLY,
+                  self._gap_start.data_ptr(), self._gap_count.data_ptr(),
+                  self._block_sums.data_ptr(), self.size, _stream())
+        total = int(self._gap_start[-1].item())
+        if total > self.size or total < 0:
+            return False
+        self._data, self._alt = self._alt, self._data
+        self._rep = "gapped"
+        self._gap_nleft = 0
+        self._gap_dirty = False
+        return True
+
+    def _dense(self):
+        """back to the dense representation every other method works on"""
+        if self._rep != "gapped":
+            return
+        nleft = self._gap_nleft
+        st = _stream()
+        _lib.call("skb_gap_densify", self._c, self._soa(self._alt),
+                  self._gap_start.data_ptr(), self._gap_count.data_ptr(),
+                  self.manifold.c, TLX, TLY, self._cell_counts_alt.data_ptr(),
+                  self._cell_counts.data_ptr(), self._tile_offsets.data_ptr(),
+                  self._block_sums.data_ptr(), self._leftover.data_ptr(),
+                  self._leftover.shape[1], nleft, self.N - nleft, st)
+        _lib.call("skb_chunk_table", self._tile_offsets.data_ptr(), self.manifold.c,
+                  TLX, TLY, CHUNK, self._chunk_first.data_ptr(), st)
+        self._data, self._alt = self._alt, self._data
+        self._rep = "dense"
+        self._n_sorted = self.N - nleft
+        # particles parked in a wrong cell (mover list overflow) break the ordering
+        self._sorted = not self._gap_dirty and self._n_sorted > 0
+        self._gap_nleft = 0
+        self._gap_dirty = False
+
+    def _push_gapped(self, E, B, dt, modified):
+        """push + boundaries + migration on the gapped layout: every cell owns a slot
+        range with slack, so only the particles that change cell are relocated (through
+        an AoS mover list); the rest are rewritten in place.  HBM traffic per particle
+        and step drops from 176 B (push + move pass of the tile sort) to ~80 B + movers.
+        Cells that run out of slots put their surplus on a small leftover list that is
+        pushed and deposited by the generic kernels and re-inserted every step; when
+        that list grows past half its size the slot ranges are rebuilt (densify ->
+        tile sort -> skb_gap_build)."""
+        if self._rep != "gapped" and not self._to_gapped():
+            return False
+        m = self.manifold
+        comm = m.comm
+        st = _stream()
+        self.time += dt
+        args, flags = self._push_args(dt, modified)
+        cnt = self._counts
+        _lib.call("skb_push_gapped", self._c, E.ptr, B.ptr, *args, flags,
+                  float(getattr(m, 'S', 0.0)), float(self.time), TLX, TLY,
+                  self._gap_start.data_ptr(), self._gap_count.data_ptr(),
+                  self._movers.data_ptr(), self._movers.shape[0],
+                  self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
+                  cnt.data_ptr(), comm.rank, comm.size, self._leftover.data_ptr(),
+                  self._leftover.shape[1], self._gap_nleft, st)
+        nm, nl, nr, fl = cnt[:4].tolist()
+        if fl & 2:
+            raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
+        nkeep = self._exchange(nl, nr)
+        new_n = self.N - nl - nr + nkeep
+        if new_n > self.size:
+            self.info[0] = new_n - self.size
+            raise RuntimeError("particle overflow error, ierr = {}".format(
+                new_n - self.size))
+        g = self._gcnt
+        g.zero_()
+        for rows, n in ((self._movers, min(nm, self._movers.shape[0])),
+                        (self._keep, nkeep)):
+            _lib.call("skb_gap_insert", rows.data_ptr(), n, self._c,
+                      self._gap_start.data_ptr(), self._gap_count.data_ptr(), m.c,
+                      self.order, TLX, TLY, self._leftover.data_ptr(),
+                      self._leftover.shape[1], g.data_ptr(), st)
+        nleft, lost = g[:2].tolist()
+        if lost:
+            raise RuntimeError("gapped layout: leftover list overflow "
+                               "({} > {})".format(nleft, self._leftover.shape[1]))
+        self._set_N_after_migration(new_n)
+        self.info[1] = self.info[2] = new_n
+        self._gap_nleft = nleft
+        self._gap_dirty = bool(fl & 1)
+        self._gap_stats = (nm, nl, nr, fl, nkeep, nleft)
+        if self._gap_dirty or 2*nleft > min(self._leftover.shape[1],
+                                            self._movers.shape[0]):
+            # slack exhausted in many cells (or parked particles): fall back to dense;
+            # the next step re-sorts and rebuilds the slot ranges around the current
+            # occupation
+            self._dense()
+        return True
 
     # -- reference API ---------------------------------------------------------------
     def initialize(self, x, y, vx, vy, vz):
         """particles.py:77-102 (positions in physical units, host arrays)"""
         m = self.manifold
+        self._rep = "dense"
         x, y, vx, vy, vz = (np.asarray(a, dtype=np.float64) for a in (x, y, vx, vy, vz))
         ind = np.logical_and(y >= m.y0 + m.edges[0]*m.dy,
                              y < m.y0 + m.edges[1]*m.dy)
@@ -306,6 +446,7 @@ class Particles:
     def move(self):
         """Move particles that left the slab to the neighbouring ranks: ppic2's
         cppmove2 (pplib2.c:607-981) as pack -> NCCL ring exchange -> unpack."""
+        self._dense()
         g = self.manifold
         comm = g.comm
         gc = g.c
@@ -417,9 +558,11 @@ class Particles:
 
     def periodic_x(self):
         """Applies periodic boundaries on particles along x"""
+        self._dense()
         _lib.call("skb_periodic_x", self._c, self.N, self.manifold.c, _stream())
 
     def calculate_ihole(self):
+        self._dense()
         _lib.call("skb_calculate_ihole", self._c, self.N, self.ihole.data_ptr(),
                   self.ntmax - 1, self.manifold.c, self._ihole_scratch.data_ptr(),
                   _stream())
@@ -432,11 +575,16 @@ class Particles:
 
     def shear_periodic_y(self):
         """Shearing periodic boundaries along y (particles.py:145-157)."""
+        self._dense()
         _lib.call("skb_shear_periodic_y", self._c, self.N, self.manifold.c,
                   float(self.manifold.S), float(self.time), _stream())
         self.periodic_y()
 
     def _push(self, E, B, dt, modified):
+        if self.gapped and self.order in (1, 2) and \
+                self._push_gapped(E, B, dt, modified):
+            return
+        self._dense()
         if self.sort_enabled and self.fused_push and self.N > 0:
             self._push_fused(E, B, dt, modified)
         else:
@@ -550,6 +698,7 @@ class Particles:
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
+        self._dense()
         self.time += dt
         qtmh = self.charge/self.mass*dt/2
         S = 0.0
@@ -586,6 +735,7 @@ class Particles:
 
     def drift(self, dt):
         """particles.py:259-265: drift, then periodic_x and periodic_y"""
+        self._dense()
         flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X
         _lib.call("skb_drift", self._c, self.N, float(dt), self.manifold.c,
                   self._epilogue(flags), _stream())

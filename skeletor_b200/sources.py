@@ -44,8 +44,14 @@ class Sources(Field):
                       self.grid.c, particles.order, float(S), particles._tiling_c(),
                       particles._cellsums().data_ptr(), _stream())
         else:
+            # (gapped layout: the tiling names the slot range of every cell, N unused)
             _lib.call("skb_deposit", particles._c, particles.N, self.ptr, self.grid.c,
                       particles.order, float(S), particles._tiling_c(), _stream())
+            if particles._rep == "gapped" and particles._gap_nleft > 0:
+                lo = particles._leftover
+                _lib.call("skb_deposit", particles._soa(lo), particles._gap_nleft,
+                          self.ptr, self.grid.c, particles.order, float(S), None,
+                          _stream())
         self.boundaries_set = False
         self.normalize(particles)
         if set_boundaries:

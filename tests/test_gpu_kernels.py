@@ -547,6 +547,81 @@ def test_fused_push_sort_equals_unfused(order, shear):
     assert np.array_equal(out[0], gu.sorted_rows(parts[0][:N[0]]))
 
 
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("shear", [False, True])
+@pytest.mark.parametrize("stress", ["none", "movers", "cells"])
+def test_gapped_layout_push_equals_oracle(order, shear, stress):
+    """Particles.gapped: push on per-cell slot ranges (skb_push_gapped + skb_gap_insert)
+    gives exactly the particles of the oracle's push + boundaries + move, the deposit
+    from the gapped arrays matches the oracle's, and the overflow paths (mover list
+    full -> parked particles, cell out of slots -> leftover list) recover"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 64, 32, 24
+    kw = dict(lbx=2, lby=2, Lx=2.0, Ly=1.0, x0=-1.0, y0=-0.5)
+    if shear:
+        m = sk.ShearingManifold(nx, ny, sk.COMM_SELF, S=-1.5, Omega=1.0, **kw)
+        g = orc.Grid(nx, ny, S=-1.5, Omega=1.0, **kw)
+    else:
+        m = sk.Manifold(nx, ny, sk.COMM_SELF, **kw)
+        g = orc.Grid(nx, ny, **kw)
+    rng = np.random.default_rng(33)
+    n = nx*ny*npc
+    x = -1.0 + rng.uniform(0, 2.0, n)
+    y = -0.5 + rng.uniform(0, 1.0, n)
+    v = rng.normal(0, 0.6, (3, n))
+    if stress == "cells":
+        # a converging flow piles particles up in a few columns: cells run out of slots
+        v[0] = -20.0*x + rng.normal(0, 0.05, n)
+    E = random_field(g, orc.Float3, rng, -0.2, 0.2)
+    B = random_field(g, orc.Float3, rng)
+    dt = 0.3*g.dx
+    nmax = int(3.2*n)
+    ions = sk.Particles(m, nmax, charge=1.0, mass=1.5, order=order)
+    ions.gapped = True
+    if stress == "movers":
+        ions._gap_alloc()
+        ions._movers = ions._movers[:4096]  # far fewer rows than movers
+    if stress == "cells":
+        ions.mover_fraction = 1.0          # only the slot ranges overflow
+    ions.initialize(x, y, v[0], v[1], v[2])
+    Ef, Bf = sk.Field(m, dtype=sk.Float3), sk.Field(m, dtype=sk.Float3)
+    Ef[...] = E
+    Bf[...] = B
+    src = sk.Sources(m)
+    p = np.zeros(nmax, orc.Particle)
+    p["x"][:n], p["y"][:n] = (x - g.x0)/g.dx, (y - g.y0)/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = v
+    parts, N, t = [p], [n], 0.0
+    reps, nleft_max = [], 0
+    for it in range(5):
+        (ions.push_modified if shear else ions.push)(Ef, Bf, dt)
+        reps.append((ions._rep,) + tuple(getattr(ions, "_gap_stats", ())))
+        nleft_max = max(nleft_max, ions._gap_nleft)
+        t += dt
+        orc.push(parts[0][:N[0]], E, B, g, order, 1.0/1.5*dt/2, dt, shear, 1.0, -1.5)
+        if shear:
+            orc.shear_periodic_y(parts[0][:N[0]], g, -1.5, t)
+        parts, N = orc.move(parts, N, [g])
+        orc.periodic_x(parts[0][:N[0]], g)
+        assert ions.N == N[0]
+        # deposit straight from the representation the push left behind
+        src.deposit(ions)
+        exp = g.field(orc.Float4)
+        orc.deposit(parts[0][:N[0]], exp, g, order, -1.5 if shear else 0.0)
+        fac = ions.charge*ions.n0*nx*ny/N[0]
+        assert rel(src.t.cpu().numpy(), exp.view(np.float64)*fac) < 1e-12
+        if it in (1, 4):
+            assert np.array_equal(gu.sorted_rows(np.asarray(ions[:ions.N])),
+                                  gu.sorted_rows(parts[0][:N[0]]))
+    if stress == "movers":
+        # parked particles: the rebuild path was taken
+        assert "dense" in [r[0] for r in reps], reps
+    else:
+        assert all(r[0] == "gapped" for r in reps[:2]), reps
+    if stress == "cells":
+        assert nleft_max > 0            # some cells did run out of slots
+
+
 def test_edge_positions_classify_exactly_like_the_reference():
     """particles sitting exactly on cell faces, slab edges and the periodic seam: the
     strict / non-strict comparisons and C truncation must match bit for bit"""

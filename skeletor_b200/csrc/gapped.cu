@@ -19,8 +19,21 @@
 #include "gather.cuh"
 
 #define GAP_THREADS 256
+#ifndef GAP_UNR
 #define GAP_UNR 2
+#endif
+#ifndef GAP_MINB
+#define GAP_MINB 3
+#endif
 
+#define GAP_BLOCK 64
+__device__ __forceinline__ void gap_cp_async16(double *smem_dst, const double *gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void gap_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gap_cp_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void gap_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void gap_prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -184,7 +197,7 @@ struct GapPush {
 };
 
 template <int ORDER, bool MODIFIED>
-__global__ void __launch_bounds__(GAP_THREADS, 2)
+__global__ void __launch_bounds__(GAP_THREADS, (ORDER == 1) ? GAP_MINB : 2)
 push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
                    const double *__restrict__ B, DevGrid g, DevTiling tl, GapPush q,
                    int parts, int wstride, int wrows) {
@@ -195,7 +208,6 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   const int cpp = (1 << cells_log2) / parts;
   const int tile = blockIdx.x / parts;
   const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
-  const int pend = tl.gap_start[c0 + cpp];
   const Window w = tile_window(tile, tl, g);
   stage_window(sE, E, w, wstride, g);
   stage_window(sB, B, w, wstride, g);
@@ -208,105 +220,139 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   // mover slots are reserved GAP_MCHUNK at a time per warp (one global atomic per chunk
   // instead of one per 32 particles on a single address)
   int mbase = 0, mused = GAP_MCHUNK;
+  // per-warp ring of two 64-particle stages filled with cp.async (16 B per lane and
+  // array: slot ranges start on multiples of 16 slots), so the loads of the next two
+  // blocks are in flight, without holding registers, while a block is pushed
+  double *ring = sB + (size_t)wstride * wrows * 3 + (size_t)wv * (2 * 5 * GAP_BLOCK);
   for (int cb = 0; cb < cpw; cb += 32) {
     const bool mine = cb + lane < cpw;
     const int my_cnt = mine ? q.gap_count[wc0 + cb + lane] : 0;
     const int my_start = mine ? tl.gap_start[wc0 + cb + lane] : 0;
     const int ncell = min(32, cpw - cb);
-    for (int j = 0; j < ncell; j++) {
-      const int cell = wc0 + cb + j;
-      const int s = __shfl_sync(SKB_FULL, my_start, j);
-      const int n = __shfl_sync(SKB_FULL, my_cnt, j);
-      {
-        int next = __shfl_sync(SKB_FULL, my_start, min(j + 1, 31));
-        if (j + 1 >= ncell) next = pend;
-        const int ahead = next + lane * 16;
-        if (ahead < min(next + 16 * 16, pend)) {
-          gap_prefetch_l2(P.x + ahead); gap_prefetch_l2(P.y + ahead);
-          gap_prefetch_l2(P.vx + ahead); gap_prefetch_l2(P.vy + ahead);
-          gap_prefetch_l2(P.vz + ahead);
-        }
-      }
-      if (n == 0) continue;
-      int wcur = 0;                                  // stayers written so far
-      for (int base = 0; base < n; base += 32 * GAP_UNR) {
-        double x[GAP_UNR], y[GAP_UNR], vx[GAP_UNR], vy[GAP_UNR], vz[GAP_UNR];
+#define GAP_CNT(j) __shfl_sync(SKB_FULL, my_cnt, (j) & 31)
+#define GAP_ADVANCE(j, base)                                   \
+  do {                                                         \
+    base += GAP_BLOCK;                                         \
+    if (base >= GAP_CNT(j)) {                                  \
+      base = 0; j++;                                           \
+      while (j < ncell && GAP_CNT(j) == 0) j++;                \
+    }                                                          \
+  } while (0)
+#define GAP_FETCH(stage, j, base)                                                       \
+  do {                                                                                  \
+    const int fs_ = __shfl_sync(SKB_FULL, my_start, (j) & 31);                          \
+    const int fi_ = (base) + 2 * lane;                                                  \
+    if (fi_ < GAP_CNT(j)) {                                                             \
+      double *d_ = ring + (stage) * (5 * GAP_BLOCK) + 2 * lane;                         \
+      const long long o_ = (long long)fs_ + fi_;                                        \
+      gap_cp_async16(d_, P.x + o_); gap_cp_async16(d_ + GAP_BLOCK, P.y + o_);           \
+      gap_cp_async16(d_ + 2 * GAP_BLOCK, P.vx + o_);                                    \
+      gap_cp_async16(d_ + 3 * GAP_BLOCK, P.vy + o_);                                    \
+      gap_cp_async16(d_ + 4 * GAP_BLOCK, P.vz + o_);                                    \
+    }                                                                                   \
+  } while (0)
+    int fj = 0, fbase = 0;
+    while (fj < ncell && GAP_CNT(fj) == 0) fj++;
+    int cj = fj, cbase = 0;
 #pragma unroll
-        for (int u = 0; u < GAP_UNR; u++) {
-          const int i = base + u * 32 + lane;
-          if (i < n) {
-            x[u] = P.x[s + i]; y[u] = P.y[s + i]; vx[u] = P.vx[s + i];
-            vy[u] = P.vy[s + i]; vz[u] = P.vz[s + i];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < GAP_UNR; u++) {
-          const int i = base + u * 32 + lane;
-          const bool act = i < n;
-          bool stay = false, mover = false;
-          if (act) {
-            fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x[u], y[u],
-                                             vx[u], vy[u], vz[u]);
-            x[u] = x[u] + vx[u] * q.dtdsx;          // drift_particle, particle_push.pxd:88-91
-            y[u] = y[u] + vy[u] * q.dtdsy;
-            if (q.flags & SKB_EPI_SHEAR) {           // particle_boundary.pyx:41-49
-              if (y[u] < 0.0) { x[u] = x[u] - q.x_boost; vx[u] = vx[u] - q.vx_boost; }
-              if (y[u] >= (double)g.ny) { x[u] = x[u] + q.x_boost; vx[u] = vx[u] + q.vx_boost; }
-            }
-            if (q.flags & SKB_EPI_PERIODIC_X) x[u] = wrap_x(x[u], nxd);
-            if (y[u] < g.e0 || y[u] >= g.e1) {       // leaves the slab: cppmove2's pack
-              double *buf; int slot; double yy = y[u];
-              if (yy < g.e0) {
-                if (q.rank == 0) yy += (double)g.ny;
-                slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
-              } else {
-                if (q.rank == q.nvp - 1) yy -= (double)g.ny;
-                slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
-              }
-              if (slot < q.nbmax) {
-                double *r = buf + (size_t)slot * 5;
-                r[0] = x[u]; r[1] = yy; r[2] = vx[u]; r[3] = vy[u]; r[4] = vz[u];
-              } else {
-                atomicOr(q.counts + 3, 2);
-              }
-            } else {
-              stay = cell_key(x[u], y[u], q.key) == cell;
-              mover = !stay;
-            }
-          }
-          // movers: one slot claim per warp
-          const unsigned mm = __ballot_sync(SKB_FULL, mover);
-          if (mm) {
-            const int k = __popc(mm), room = GAP_MCHUNK - mused;
-            int nb = mbase;
-            if (k > room) {
-              if (lane == 0) nb = atomicAdd(q.counts + 0, GAP_MCHUNK);
-              nb = __shfl_sync(SKB_FULL, nb, 0);
-            }
-            if (mover) {
-              const int r = __popc(mm & lt);
-              const int slot = r < room ? mbase + mused + r : nb + (r - room);
-              if (slot < q.mover_cap) {
-                double *r = q.movers + (size_t)slot * 5;
-                r[0] = x[u]; r[1] = y[u]; r[2] = vx[u]; r[3] = vy[u]; r[4] = vz[u];
-              } else {
-                stay = true;                         // list full: park it here, rebuild later
-                atomicOr(q.counts + 3, 1);
-              }
-            }
-            if (k > room) { mbase = nb; mused = k - room; } else mused += k;
-          }
-          // stayers: compacted to the front of the cell's range
-          const unsigned sm = __ballot_sync(SKB_FULL, stay);
-          if (stay) {
-            const int d = s + wcur + __popc(sm & lt);
-            P.x[d] = x[u]; P.y[d] = y[u]; P.vx[d] = vx[u]; P.vy[d] = vy[u]; P.vz[d] = vz[u];
-          }
-          wcur += __popc(sm);
-        }
-      }
-      if (lane == 0) q.gap_count[cell] = wcur;
+    for (int st = 0; st < 2; st++) {
+      if (fj < ncell) { GAP_FETCH(st, fj, fbase); GAP_ADVANCE(fj, fbase); }
+      gap_cp_commit();
     }
+    int stage = 0, wcur = 0;                         // wcur: stayers written so far
+    while (cj < ncell) {
+      const int cell = wc0 + cb + cj;
+      const int s = __shfl_sync(SKB_FULL, my_start, cj);
+      const int n = GAP_CNT(cj);
+      gap_cp_wait_one();
+      __syncwarp();
+      const double *pb = ring + stage * (5 * GAP_BLOCK);
+#pragma unroll 1
+      for (int u = 0; u < GAP_BLOCK / 32; u++) {
+        if (cbase + u * 32 >= n) break;
+        const int i = cbase + u * 32 + lane;
+        const bool act = i < n;
+        bool stay = false, mover = false;
+        double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+        if (act) {
+          const double *pp = pb + u * 32 + lane;
+          x = pp[0]; y = pp[GAP_BLOCK]; vx = pp[2 * GAP_BLOCK]; vy = pp[3 * GAP_BLOCK];
+          vz = pp[4 * GAP_BLOCK];
+          fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
+          x = x + vx * q.dtdsx;                      // drift_particle, particle_push.pxd:88-91
+          y = y + vy * q.dtdsy;
+          if (q.flags & SKB_EPI_SHEAR) {             // particle_boundary.pyx:41-49
+            if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
+            if (y >= (double)g.ny) { x = x + q.x_boost; vx = vx + q.vx_boost; }
+          }
+          if (q.flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, nxd);
+          if (y < g.e0 || y >= g.e1) {               // leaves the slab: cppmove2's pack
+            double *buf; int slot; double yy = y;
+            if (yy < g.e0) {
+              if (q.rank == 0) yy += (double)g.ny;
+              slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
+            } else {
+              if (q.rank == q.nvp - 1) yy -= (double)g.ny;
+              slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
+            }
+            if (slot < q.nbmax) {
+              double *r = buf + (size_t)slot * 5;
+              r[0] = x; r[1] = yy; r[2] = vx; r[3] = vy; r[4] = vz;
+            } else {
+              atomicOr(q.counts + 3, 2);
+            }
+          } else {
+            stay = cell_key(x, y, q.key) == cell;
+            mover = !stay;
+          }
+        }
+        // movers: slots from the warp's reservation
+        const unsigned mm = __ballot_sync(SKB_FULL, mover);
+        if (mm) {
+          const int k = __popc(mm), room = GAP_MCHUNK - mused;
+          int nb = mbase;
+          if (k > room) {
+            if (lane == 0) nb = atomicAdd(q.counts + 0, GAP_MCHUNK);
+            nb = __shfl_sync(SKB_FULL, nb, 0);
+          }
+          if (mover) {
+            const int r = __popc(mm & lt);
+            const int slot = r < room ? mbase + mused + r : nb + (r - room);
+            if (slot < q.mover_cap) {
+              double *o = q.movers + (size_t)slot * 5;
+              o[0] = x; o[1] = y; o[2] = vx; o[3] = vy; o[4] = vz;
+            } else {
+              stay = true;                           // list full: park it here, rebuild later
+              atomicOr(q.counts + 3, 1);
+            }
+          }
+          if (k > room) { mbase = nb; mused = k - room; } else mused += k;
+        }
+        // stayers: compacted to the front of the cell's range (always behind the reads:
+        // wcur <= cbase + u*32, and the blocks in flight start at cbase + 64 or later)
+        const unsigned sm = __ballot_sync(SKB_FULL, stay);
+        if (stay) {
+          const long long d = (long long)s + wcur + __popc(sm & lt);
+          P.x[d] = x; P.y[d] = y; P.vx[d] = vx; P.vy[d] = vy; P.vz[d] = vz;
+        }
+        wcur += __popc(sm);
+      }
+      __syncwarp();                                  // stage fully read: refill it
+      int nj = cj, nbase = cbase;
+      GAP_ADVANCE(nj, nbase);
+      if (nj != cj) {
+        if (lane == 0) q.gap_count[cell] = wcur;
+        wcur = 0;
+      }
+      cj = nj; cbase = nbase;
+      if (fj < ncell) { GAP_FETCH(stage, fj, fbase); GAP_ADVANCE(fj, fbase); }
+      gap_cp_commit();
+      stage ^= 1;
+    }
+    gap_cp_wait_all();
+#undef GAP_CNT
+#undef GAP_ADVANCE
+#undef GAP_FETCH
   }
   // unused tail of this warp's last reservation: padding rows
   for (int r = mused + lane; r < GAP_MCHUNK; r += 32)
@@ -413,7 +459,14 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
   int parts = 1;
   while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
   const int ws = window_stride(tl), wr = window_rows(tl);
-  const size_t smem = (size_t)ws * wr * 3 * 2 * sizeof(double);
+  // E and B windows + the warps' particle rings
+  const size_t smem = ((size_t)ws * wr * 3 * 2 + (GAP_THREADS / 32) * 2 * 5 * GAP_BLOCK) *
+                      sizeof(double);
+  // 16-byte cp.async: the five arrays must be 16-byte aligned (and every gap_start even,
+  // as skb_gap_build guarantees)
+  if ((((uintptr_t)p.x | (uintptr_t)p.y | (uintptr_t)p.vx | (uintptr_t)p.vy |
+        (uintptr_t)p.vz) & 15) != 0)
+    return (int)cudaErrorMisalignedAddress;
   void (*k)(skb_particles_t, const double *, const double *, DevGrid, DevTiling, GapPush,
             int, int, int);
   if (order == 1) k = modified ? push_gapped_kernel<1, true> : push_gapped_kernel<1, false>;

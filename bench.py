@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--ny", type=int, default=NY)
     ap.add_argument("--ppc", type=int, default=PPC)
     ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--layout", default="gapped", choices=["gapped", "dense"],
+                    help="particle layout: per-cell slot ranges with slack (default) or "
+                         "dense arrays re-ordered by the tile sort every step")
     ap.add_argument("--perturbed", action="store_true",
                     help="5 %% sinusoidal density contrast along x (SURVEY.md 8d)")
     ap.add_argument("--weak", action="store_true",
@@ -171,9 +174,12 @@ def b200_arm(a):
                     lby=1 if a.order == 1 else 2, Lx=1.0, Ly=a.ny/a.nx)
     n_local = a.nx*m.nyp*a.ppc
     n_total = a.nx*a.ny*a.ppc
-    nmax = int(1.05*n_local) + 4096
+    gapped = a.layout == "gapped"
+    nmax = int((1.36 if gapped else 1.05)*n_local) + 4096
+    nmax += nmax & 1
     ions = sk.Particles(m, nmax, charge=1.0, mass=1.0, order=a.order,
                         nbmax=max(n_local//100, 1 << 16))
+    ions.gapped = gapped
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     d = ions._data
@@ -237,6 +243,32 @@ def b200_arm(a):
     # ---- per-kernel roofline: instrumented pass, CUDA events around each C-ABI call
     peak, peak_src = measured_peak()
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    # (g) gapped layout, the default step: push on per-cell slot ranges (movers parked
+    #     and re-inserted by the kernel itself) | migration + insertion of the rest |
+    #     deposit | guards
+    accg, nlocal = None, 0
+    if gapped and ions._rep == "gapped":
+        accg = {"push": [], "migrate_insert": [], "deposit": [], "guards": []}
+        for _ in range(3):
+            if ions._rep != "gapped" and not ions._to_gapped():
+                break
+            t = [ev() for _ in range(5)]
+            torch.cuda.synchronize()
+            t[0].record(); cnt = ions._gap_kernel(E, B, dt, False)
+            t[1].record(); ions._gap_finish(cnt)
+            t[2].record()
+            src.t.zero_()
+            _lib.call("skb_deposit", ions._c, ions.N, src.ptr, m.c, ions.order, 0.0,
+                      ions._tiling_c(), torch.cuda.current_stream().cuda_stream)
+            t[3].record()
+            src.boundaries_set = False
+            src.normalize(ions); src.add_guards(); src.copy_guards()
+            t[4].record()
+            torch.cuda.synchronize()
+            nlocal = ions._gap_stats[6]
+            for name, i in zip(accg, range(4)):
+                accg[name].append(t[i].elapsed_time(t[i + 1]))
+        ions._dense()
     # (a) the step as it runs by default: push (+ fused boundary epilogue and sort
     #     histogram) | migration | precounted tile sort | deposit | guards
     st_ = lambda: torch.cuda.current_stream().cuda_stream
@@ -326,12 +358,20 @@ def b200_arm(a):
                 out[name].update({"alg_bytes": alg[name], "achieved_gbs": round(gbs, 1),
                                   "frac": round(gbs/peak, 4)})
         return out
-    kern = summarize(acc)
+    standalone = summarize(acc2)
+    if accg and all(accg.values()):
+        standalone.update({"dense_" + k: v for k, v in summarize(acc).items()})
+        # in-place movers are read and written twice: + 80 B each
+        alg["push"] = 80.0*npart + 80.0*nlocal + 48.0*cells
+        kern = summarize(accg)
+        candidates, tkey = ("push", "deposit"), {"push": "push_gapped"}
+    else:
+        kern = summarize(acc)
+        candidates, tkey = ("push", "tile_sort", "deposit"), {}
     step_ms = sum(v["ms"] for v in kern.values())
     for v in kern.values():
         v["share"] = round(v["ms"]/step_ms, 4)
-    standalone = summarize(acc2)
-    dom = max(("push", "tile_sort", "deposit"), key=lambda k: kern[k]["ms"])
+    dom = max(candidates, key=lambda k: kern[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": None, "peak_source": peak_src,
@@ -340,7 +380,7 @@ def b200_arm(a):
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(dom)
+            roofline["traffic"] = json.load(open(tr)).get(tkey.get(dom, dom))
         except Exception:
             pass
 
@@ -388,7 +428,9 @@ def b200_arm(a):
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms/a.steps,
                 "higher_is_better": True, "scaling": "weak" if a.weak else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(a, {"particles_per_gpu": n_local}),
+                "config": workload_config(a, {"particles_per_gpu": n_local,
+                                              "layout": a.layout if not gapped else
+                                              ("gapped" if accg else "dense (fallback)")}),
                 "roofline": roofline, "kernels": kern, "alternative_kernels": standalone, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}
         print(json.dumps(line), flush=True)

@@ -262,11 +262,17 @@ int skb_canonical_cells(skb_particles_t in, skb_particles_t out, const int *cell
  * skb_push_gapped: push (+ shear boost / x wrap: epi_flags, epi_S, epi_t) of every cell's
  *   particles; stayers are written back compacted into their own range, particles that
  *   change cell go to `movers` (AoS rows; counts[0]), particles that leave the slab to
- *   sbufl / sbufr as skb_move_pack would (counts[1], counts[2]); counts[3] = flags
+ *   sbufl / sbufr as skb_move_pack would (counts[1], counts[2]); counts[4] = movers
+ *   re-inserted in place (statistics); counts[3] = flags
  *   (1: mover list full, some particles were parked in their old cell -> rebuild;
  *    2: exchange buffer overflow).
  *   The nleft particles of `leftover` (below) are pushed first, with the generic
  *   kernel, and join the head of the mover list (nleft <= mover_cap).
+ *   Movers whose new cell is handled by the same thread block never reach `movers`:
+ *   the block parks them in one of npool scratch blocks ([npool][scratch_rows][5]
+ *   doubles, pool_owner [npool] zero-initialised; npool >= 592 or 0 to disable) and
+ *   inserts them itself; full cells overflow into `leftover` (leftover_counts[0] rows,
+ *   [1] overflow flag; both reset by this call after the old leftovers are consumed).
  * skb_gap_insert:  drop AoS rows (movers, arrivals) into the free slots of their cells;
  *   rows that do not fit go to `leftover`, a small SoA list [5][leftover_cap]
  *   (counts[0] rows; counts[1] = leftover overflow) that lives beside the cells until
@@ -283,7 +289,8 @@ int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
                     double epi_t, int tlx, int tly, const int *gap_start, int *gap_count,
                     double *movers, int mover_cap, double *sbufl, double *sbufr,
                     int nbmax, int *counts, int rank, int nvp, double *leftover,
-                    int leftover_cap, int nleft, void *stream);
+                    int leftover_cap, int nleft, int *leftover_counts, double *scratch,
+                    int scratch_rows, int npool, int *pool_owner, void *stream);
 int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
                    int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
                    double *leftover, int leftover_cap, int *counts, void *stream);

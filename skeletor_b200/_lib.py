@@ -81,7 +81,8 @@ SIGNATURES = {
     "skb_gap_build": [_P, _P, c_vp, _G, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_vp],
     "skb_push_gapped": [_P, c_vp, c_vp, _G, c_int, c_dbl, c_dbl, c_int, c_dbl, c_dbl,
                         c_int, c_dbl, c_dbl, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp,
-                        c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
+                        c_vp, c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp,
+                        c_vp, c_int, c_int, c_vp, c_vp],
     "skb_gap_insert": [c_vp, c_int, _P, c_vp, c_vp, _G, c_int, c_int, c_int, c_vp, c_int,
                        c_vp, c_vp],
     "skb_gap_densify": [_P, _P, c_vp, c_vp, _G, c_int, c_int, c_vp, c_vp, c_vp, c_vp,

@@ -15,6 +15,7 @@
 // caller rebuilds the layout through the dense path (densify -> tile sort -> build).
 //
 // New component (no reference counterpart); ordering stays a performance property.
+#include <cstdlib>
 #include "common.cuh"
 #include "gather.cuh"
 
@@ -46,7 +47,9 @@ gap_caps_kernel(const int *__restrict__ cell_end, int ncells, int *gap_start) {
   if (c > ncells) return;
   if (c == ncells) { gap_start[c] = 0; return; }
   const int n = cell_end[c] - (c ? cell_end[c - 1] : 0);
-  gap_start[c] = (n + max(16, n >> 2) + 15) & ~15;
+  // 25 % slack; big cells start on 128-byte lines, small ones only on even slots (the
+  // 16-byte cp.async of the push needs that much)
+  gap_start[c] = n < 64 ? (n + max(4, n >> 2) + 3) & ~3 : (n + (n >> 2) + 15) & ~15;
 }
 
 // dense (cell_end) -> gapped (gap_start already scanned); one warp per cell
@@ -137,46 +140,64 @@ gap_route_kernel(const double *__restrict__ lo, int cap, int n, double e0, doubl
 
 // One slot claim per warp and destination cell (rows arrive roughly ordered by source
 // tile, so a warp sees few distinct cells and its writes into one cell are contiguous).
+#define GAP_INS_ITEMS 4
 __global__ void __launch_bounds__(256)
 gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
                   const int *__restrict__ gap_start, int *gap_count, KeyParams kp,
                   double *leftover, int leftover_cap, int *counts) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  // GAP_INS_ITEMS independent rows per thread: the row load -> slot claim -> store
+  // chains overlap instead of adding up
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-  bool valid = i < n;
-  if (valid) {
-    const double *r = rows + (size_t)i * 5;
-    r0 = r[0]; r1 = r[1]; r2 = r[2]; r3 = r[3]; r4 = r[4];
-    valid = __double_as_longlong(r0) != GAP_PAD_BITS;
+  const int i0 = blockIdx.x * (256 * GAP_INS_ITEMS) + threadIdx.x;
+  double r0[GAP_INS_ITEMS], r1[GAP_INS_ITEMS], r2[GAP_INS_ITEMS], r3[GAP_INS_ITEMS],
+      r4[GAP_INS_ITEMS];
+  bool valid[GAP_INS_ITEMS];
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    const int i = i0 + t * 256;
+    valid[t] = i < n;
+    r0[t] = r1[t] = r2[t] = r3[t] = r4[t] = 0.0;
+    if (valid[t]) {
+      const double *r = rows + (size_t)i * 5;
+      r0[t] = r[0]; r1[t] = r[1]; r2[t] = r[2]; r3[t] = r[3]; r4[t] = r[4];
+    }
   }
-  const int key = valid ? cell_key(r0, r1, kp) : -1 - lane;
-  const unsigned peers = __match_any_sync(SKB_FULL, key);
-  const int leader = __ffs(peers) - 1, rank = __popc(peers & lt), cnt = __popc(peers);
-  int s = 0, cap = 0, base = 0;
-  if (valid && lane == leader) {
-    s = gap_start[key]; cap = gap_start[key + 1] - s;
-    base = atomicAdd(gap_count + key, cnt);
-    const int over = min(max(base + cnt - cap, 0), cnt);
-    if (over) atomicSub(gap_count + key, over);  // cell full: those go to the leftovers
+  int s[GAP_INS_ITEMS], cap[GAP_INS_ITEMS], base[GAP_INS_ITEMS], rank[GAP_INS_ITEMS],
+      leader[GAP_INS_ITEMS];
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    valid[t] = valid[t] && __double_as_longlong(r0[t]) != GAP_PAD_BITS;
+    const int key = valid[t] ? cell_key(r0[t], r1[t], kp) : -1 - lane;
+    const unsigned peers = __match_any_sync(SKB_FULL, key);
+    const int cnt = __popc(peers);
+    leader[t] = __ffs(peers) - 1; rank[t] = __popc(peers & lt);
+    s[t] = cap[t] = base[t] = 0;
+    if (valid[t] && lane == leader[t]) {
+      base[t] = atomicAdd(gap_count + key, cnt);
+      s[t] = gap_start[key]; cap[t] = gap_start[key + 1] - s[t];
+      const int over = min(max(base[t] + cnt - cap[t], 0), cnt);
+      if (over) atomicSub(gap_count + key, over);  // cell full: those go to the leftovers
+    }
   }
-  s = __shfl_sync(SKB_FULL, s, leader);
-  cap = __shfl_sync(SKB_FULL, cap, leader);
-  base = __shfl_sync(SKB_FULL, base, leader);
-  if (!valid) return;
-  const int slot = base + rank;
-  if (slot < cap) {
-    const long long d = (long long)s + slot;
-    P.x[d] = r0; P.y[d] = r1; P.vx[d] = r2; P.vy[d] = r3; P.vz[d] = r4;
-  } else {
-    const int l = atomicAdd(counts + 0, 1);
-    if (l < leftover_cap) {
-      const size_t lc = (size_t)leftover_cap;
-      leftover[l] = r0; leftover[lc + l] = r1; leftover[2 * lc + l] = r2;
-      leftover[3 * lc + l] = r3; leftover[4 * lc + l] = r4;
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    const int ss = __shfl_sync(SKB_FULL, s[t], leader[t]);
+    const int cc = __shfl_sync(SKB_FULL, cap[t], leader[t]);
+    const int slot = __shfl_sync(SKB_FULL, base[t], leader[t]) + rank[t];
+    if (!valid[t]) continue;
+    if (slot < cc) {
+      const long long d = (long long)ss + slot;
+      P.x[d] = r0[t]; P.y[d] = r1[t]; P.vx[d] = r2[t]; P.vy[d] = r3[t]; P.vz[d] = r4[t];
     } else {
-      counts[1] = 1;                            // even the leftover list is full
+      const int l = atomicAdd(counts + 0, 1);
+      if (l < leftover_cap) {
+        const size_t lc = (size_t)leftover_cap;
+        leftover[l] = r0[t]; leftover[lc + l] = r1[t]; leftover[2 * lc + l] = r2[t];
+        leftover[3 * lc + l] = r3[t]; leftover[4 * lc + l] = r4[t];
+      } else {
+        counts[1] = 1;                            // even the leftover list is full
+      }
     }
   }
 }
@@ -193,7 +214,18 @@ struct GapPush {
   double *sbufl, *sbufr;
   int nbmax, rank, nvp;
   int *counts;               // [0] movers, [1] sbufl, [2] sbufr, [3] flags (1: mover list
-                             // full -> some particles sit in the wrong cell, 2: nbmax)
+                             // full -> some particles sit in the wrong cell, 2: nbmax),
+                             // [4] movers re-inserted by their own block
+  // movers whose new cell belongs to the same CTA are parked in a scratch block (claimed
+  // from a pool for the lifetime of the CTA, L2 resident) and dropped into their cells
+  // by the CTA itself once all its cells are compacted
+  double *scratch;           // [npool][scratch_rows][5]
+  int scratch_rows, npool;
+  int *pool_owner;           // [npool] 0 = free
+  const int *gap_start;
+  double *leftover;          // SoA [5][leftover_cap]: rows whose cell is full
+  int leftover_cap;
+  int *lcounts;              // [0] leftover rows, [1] leftover overflow
 };
 
 template <int ORDER, bool MODIFIED>
@@ -209,9 +241,20 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   const int tile = blockIdx.x / parts;
   const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
   const Window w = tile_window(tile, tl, g);
+  __shared__ int s_blk, s_nrows;
+  if (threadIdx.x == 0) {
+    int b = -1;
+    if (q.npool > 0) {
+      b = blockIdx.x % q.npool;
+      while (atomicCAS(q.pool_owner + b, 0, 1) != 0) b = (b + 1 == q.npool) ? 0 : b + 1;
+    }
+    s_blk = b; s_nrows = 0;
+  }
   stage_window(sE, E, w, wstride, g);
   stage_window(sB, B, w, wstride, g);
   __syncthreads();
+  double *const scr = s_blk >= 0 ? q.scratch + (size_t)s_blk * q.scratch_rows * 5 : nullptr;
+  const int scr_rows = s_blk >= 0 ? q.scratch_rows : 0;
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const int cpw = cpp / (GAP_THREADS / 32);
@@ -272,7 +315,7 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
         if (cbase + u * 32 >= n) break;
         const int i = cbase + u * 32 + lane;
         const bool act = i < n;
-        bool stay = false, mover = false;
+        bool stay = false, mover = false, local = false;
         double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
         if (act) {
           const double *pp = pb + u * 32 + lane;
@@ -302,11 +345,28 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
               atomicOr(q.counts + 3, 2);
             }
           } else {
-            stay = cell_key(x, y, q.key) == cell;
+            const int dk = cell_key(x, y, q.key);
+            stay = dk == cell;
             mover = !stay;
+            local = mover && (unsigned)(dk - c0) < (unsigned)cpp;
           }
         }
-        // movers: slots from the warp's reservation
+        // movers inside this CTA's cell range: scratch block
+        const unsigned lm = __ballot_sync(SKB_FULL, local && scr_rows > 0);
+        if (lm) {
+          int b0 = 0;
+          if (lane == __ffs(lm) - 1) b0 = atomicAdd(&s_nrows, __popc(lm));
+          b0 = __shfl_sync(SKB_FULL, b0, __ffs(lm) - 1);
+          if (local) {
+            const int slot = b0 + __popc(lm & lt);
+            if (slot < scr_rows) {
+              double *o = scr + (size_t)slot * 5;
+              o[0] = x; o[1] = y; o[2] = vx; o[3] = vy; o[4] = vz;
+              mover = false;
+            }
+          }
+        }
+        // the other movers: global list, slots from the warp's reservation
         const unsigned mm = __ballot_sync(SKB_FULL, mover);
         if (mm) {
           const int k = __popc(mm), room = GAP_MCHUNK - mused;
@@ -353,6 +413,51 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
 #undef GAP_CNT
 #undef GAP_ADVANCE
 #undef GAP_FETCH
+  }
+  // phase B: all cells of this CTA are compacted; drop the parked movers into them
+  __syncthreads();
+  if (scr_rows > 0) {
+    const int nrows = min(s_nrows, scr_rows);
+    if (threadIdx.x == 0 && nrows) atomicAdd(q.counts + 4, nrows);   // statistics
+    for (int r0 = (int)(threadIdx.x & ~31); r0 < nrows; r0 += GAP_THREADS) {
+      const int r = r0 + lane;
+      const bool valid = r < nrows;
+      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+      if (valid) {
+        const double *o = scr + (size_t)r * 5;
+        x = o[0]; y = o[1]; vx = o[2]; vy = o[3]; vz = o[4];
+      }
+      const int key = valid ? cell_key(x, y, q.key) : -1 - lane;
+      const unsigned peers = __match_any_sync(SKB_FULL, key);
+      const int leader = __ffs(peers) - 1, cnt = __popc(peers);
+      int s = 0, cap = 0, base = 0;
+      if (valid && lane == leader) {
+        base = atomicAdd(q.gap_count + key, cnt);
+        s = q.gap_start[key]; cap = q.gap_start[key + 1] - s;
+        const int over = min(max(base + cnt - cap, 0), cnt);
+        if (over) atomicSub(q.gap_count + key, over);
+      }
+      s = __shfl_sync(SKB_FULL, s, leader);
+      cap = __shfl_sync(SKB_FULL, cap, leader);
+      const int slot = __shfl_sync(SKB_FULL, base, leader) + __popc(peers & lt);
+      if (valid) {
+        if (slot < cap) {
+          const long long d = (long long)s + slot;
+          P.x[d] = x; P.y[d] = y; P.vx[d] = vx; P.vy[d] = vy; P.vz[d] = vz;
+        } else {
+          const int l = atomicAdd(q.lcounts + 0, 1);
+          if (l < q.leftover_cap) {
+            const size_t lc = (size_t)q.leftover_cap;
+            q.leftover[l] = x; q.leftover[lc + l] = y; q.leftover[2 * lc + l] = vx;
+            q.leftover[3 * lc + l] = vy; q.leftover[4 * lc + l] = vz;
+          } else {
+            q.lcounts[1] = 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(q.pool_owner + s_blk, 0);
   }
   // unused tail of this warp's last reservation: padding rows
   for (int r = mused + lane; r < GAP_MCHUNK; r += 32)
@@ -420,7 +525,8 @@ extern "C" int skb_gap_insert(const double *rows, int n, skb_particles_t p,
   if (n <= 0) return 0;
   DevGrid g = make_grid(grid);
   KeyParams kp = make_keyparams(g, order, tlx, tly);
-  gap_insert_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  const int per = 256 * GAP_INS_ITEMS;
+  gap_insert_kernel<<<(n + per - 1) / per, 256, 0, (cudaStream_t)stream>>>(
       rows, n, p, gap_start, gap_count, kp, leftover, leftover_cap, counts);
   SKB_CHECK_LAUNCH();
   return 0;
@@ -433,7 +539,9 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
                                const int *gap_start, int *gap_count, double *movers,
                                int mover_cap, double *sbufl, double *sbufr, int nbmax,
                                int *counts, int rank, int nvp, double *leftover,
-                               int leftover_cap, int nleft, void *stream) {
+                               int leftover_cap, int nleft, int *leftover_counts,
+                               double *scratch, int scratch_rows, int npool,
+                               int *pool_owner, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
   DevGrid g = make_grid(grid);
@@ -452,12 +560,27 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
   q.gap_count = gap_count; q.movers = movers; q.mover_cap = mover_cap;
   q.sbufl = sbufl; q.sbufr = sbufr; q.nbmax = nbmax; q.rank = rank; q.nvp = nvp;
   q.counts = counts;
-  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
+  q.scratch = scratch; q.scratch_rows = scratch_rows;
+  q.npool = (scratch && pool_owner && scratch_rows > 0) ? npool : 0;
+  q.pool_owner = pool_owner; q.gap_start = gap_start;
+  q.leftover = leftover; q.leftover_cap = leftover_cap; q.lcounts = leftover_counts;
+  // more blocks than CTAs can ever be resident, or the claim loop could spin forever
+  if (q.npool > 0 && q.npool < 148 * 4) return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
+  if (q.npool > 0) {       // (all blocks free: a failed earlier launch cannot leave claims)
+    e = cudaMemsetAsync(pool_owner, 0, sizeof(int) * (size_t)q.npool, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   const int ntiles = t.ntx * t.nty;
   const int cells = 1 << (tlx + tly);
-  int parts = 1;
+  // at least two blocks per tile: the parked movers of the resident blocks then fit L2
+  int parts = cells >= 32 ? 2 : 1;
   while (parts < cells / 8 && (long long)ntiles * parts < 8 * 148) parts <<= 1;
+  if (const char *ev = getenv("SKB_GAP_PARTS")) {          // tuning aid
+    const int pv = atoi(ev);
+    if (pv >= 1 && pv <= cells / 8 && (pv & (pv - 1)) == 0) parts = pv;
+  }
   const int ws = window_stride(tl), wr = window_rows(tl);
   // E and B windows + the warps' particle rings
   const size_t smem = ((size_t)ws * wr * 3 * 2 + (GAP_THREADS / 32) * 2 * 5 * GAP_BLOCK) *
@@ -493,6 +616,10 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
         sbufr, nbmax, counts);
     SKB_CHECK_LAUNCH();
   }
+  // the old leftovers are consumed: the list restarts (this kernel and the
+  // skb_gap_insert calls that follow append to it)
+  e = cudaMemsetAsync(leftover_counts, 0, 2 * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
   k<<<ntiles * parts, GAP_THREADS, smem, st>>>(p, E, B, g, tl, q, parts, ws, wr);
   SKB_CHECK_LAUNCH();
   return 0;

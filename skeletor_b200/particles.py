@@ -14,6 +14,7 @@ same-cell particles in registers.  The ordering is a performance property only:
 kernels are correct for any order (user code may overwrite coordinates at will).
 """
 import ctypes as C
+import os
 from warnings import warn
 
 import numpy as np
@@ -152,8 +153,8 @@ class Particles:
         # gapped layout (see _push_gapped): particles stay ordered without a full move
         # pass.  Needs Nmax >= ~1.3 N; push()/push_modified() fall back to the dense
         # path when the slot ranges do not fit.
-        self.gapped = False
-        self.mover_fraction = 0.25    # size of the mover list relative to Nmax
+        self.gapped = os.environ.get("SKELETOR_B200_GAPPED", "0") == "1"
+        self.mover_fraction = 0.1     # size of the global mover list relative to Nmax
         self._rep = "dense"
         self._gap_start = None
         self._gap_nleft = 0
@@ -312,6 +313,13 @@ class Particles:
             # the cells, pushed / deposited by the generic kernels
             self._leftover = torch.zeros((5, max(mcap//8, 1024)), **f64)
             self._gcnt = torch.zeros(8, **i32)
+            # scratch blocks for the movers a thread block re-inserts itself: sized for
+            # ~3x the expected in-block movers of a uniform plasma
+            ncta = max(ntiles, min(2368, 32*ntiles))
+            self._scr_rows = int(min(max(1024, 0.5*self.size/ncta), 1 << 16))
+            self._npool = 1024
+            self._scratch = torch.zeros((self._npool, self._scr_rows, 5), **f64)
+            self._pool_owner = torch.zeros(self._npool, **i32)
 
     def _to_gapped(self):
         """dense ordered arrays -> per-cell slot ranges with slack (skb_gap_build).
@@ -358,18 +366,23 @@ class Particles:
 
     def _push_gapped(self, E, B, dt, modified):
         """push + boundaries + migration on the gapped layout: every cell owns a slot
-        range with slack, so only the particles that change cell are relocated (through
-        an AoS mover list); the rest are rewritten in place.  HBM traffic per particle
-        and step drops from 176 B (push + move pass of the tile sort) to ~80 B + movers.
-        Cells that run out of slots put their surplus on a small leftover list that is
-        pushed and deposited by the generic kernels and re-inserted every step; when
-        that list grows past half its size the slot ranges are rebuilt (densify ->
+        range with slack, so only the particles that change cell are relocated; the
+        rest are rewritten in place.  Movers that stay inside the cell range of their
+        thread block are re-inserted by the block itself (L2-resident scratch), the
+        others and the arrivals go through an AoS list and skb_gap_insert.  HBM traffic
+        per particle and step drops from 176 B (push + move pass of the tile sort) to
+        ~100 B.  Cells that run out of slots put their surplus on a small leftover list
+        that is pushed and deposited by the generic kernels and re-inserted every step;
+        when that list grows past half its size the slot ranges are rebuilt (densify ->
         tile sort -> skb_gap_build)."""
         if self._rep != "gapped" and not self._to_gapped():
             return False
+        self._gap_finish(self._gap_kernel(E, B, dt, modified))
+        return True
+
+    def _gap_kernel(self, E, B, dt, modified):
         m = self.manifold
         comm = m.comm
-        st = _stream()
         self.time += dt
         args, flags = self._push_args(dt, modified)
         cnt = self._counts
@@ -379,8 +392,15 @@ class Particles:
                   self._movers.data_ptr(), self._movers.shape[0],
                   self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
                   cnt.data_ptr(), comm.rank, comm.size, self._leftover.data_ptr(),
-                  self._leftover.shape[1], self._gap_nleft, st)
-        nm, nl, nr, fl = cnt[:4].tolist()
+                  self._leftover.shape[1], self._gap_nleft, self._gcnt.data_ptr(),
+                  self._scratch.data_ptr(), self._scr_rows, self._npool,
+                  self._pool_owner.data_ptr(), _stream())
+        return cnt
+
+    def _gap_finish(self, cnt):
+        m = self.manifold
+        st = _stream()
+        nm, nl, nr, fl, nlocal = cnt[:5].tolist()
         if fl & 2:
             raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
         nkeep = self._exchange(nl, nr)
@@ -389,8 +409,7 @@ class Particles:
             self.info[0] = new_n - self.size
             raise RuntimeError("particle overflow error, ierr = {}".format(
                 new_n - self.size))
-        g = self._gcnt
-        g.zero_()
+        g = self._gcnt          # (reset by skb_push_gapped)
         for rows, n in ((self._movers, min(nm, self._movers.shape[0])),
                         (self._keep, nkeep)):
             _lib.call("skb_gap_insert", rows.data_ptr(), n, self._c,
@@ -405,14 +424,15 @@ class Particles:
         self.info[1] = self.info[2] = new_n
         self._gap_nleft = nleft
         self._gap_dirty = bool(fl & 1)
-        self._gap_stats = (nm, nl, nr, fl, nkeep, nleft)
+        # rows on the global list (incl. padding), leavers, flags, arrivals, leftovers,
+        # movers re-inserted in place
+        self._gap_stats = (nm, nl, nr, fl, nkeep, nleft, nlocal)
         if self._gap_dirty or 2*nleft > min(self._leftover.shape[1],
                                             self._movers.shape[0]):
             # slack exhausted in many cells (or parked particles): fall back to dense;
             # the next step re-sorts and rebuilds the slot ranges around the current
             # occupation
             self._dense()
-        return True
 
     # -- reference API ---------------------------------------------------------------
     def initialize(self, x, y, vx, vy, vz):
@@ -660,6 +680,7 @@ class Particles:
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
         m = self.manifold
+        self._dense()
         # Update time
         self.time += dt
         qtmh = self.charge/self.mass*dt/2

@@ -581,6 +581,7 @@ def test_gapped_layout_push_equals_oracle(order, shear, stress):
     if stress == "movers":
         ions._gap_alloc()
         ions._movers = ions._movers[:4096]  # far fewer rows than movers
+        ions._npool = 0                     # and no block-local re-insertion
     if stress == "cells":
         ions.mover_fraction = 1.0          # only the slot ranges overflow
     ions.initialize(x, y, v[0], v[1], v[2])

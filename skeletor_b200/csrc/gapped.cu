@@ -260,6 +260,9 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   const int cpw = cpp / (GAP_THREADS / 32);
   const int wc0 = c0 + wv * cpw;
   const double nxd = (double)g.nx;
+  const int mxm = (1 << tl.tlx) - 1, mym = (1 << tl.tly) - 1;
+  const int tile_x0 = (tile % q.key.ntx) << tl.tlx, tile_y0 = (tile / q.key.ntx) << tl.tly;
+  const int part_off = (blockIdx.x % parts) * cpp;
   // mover slots are reserved GAP_MCHUNK at a time per warp (one global atomic per chunk
   // instead of one per 32 particles on a single address)
   int mbase = 0, mused = GAP_MCHUNK;
@@ -305,6 +308,8 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
     int stage = 0, wcur = 0;                         // wcur: stayers written so far
     while (cj < ncell) {
       const int cell = wc0 + cb + cj;
+      const int cix = tile_x0 + ((cell - (tile << cells_log2)) & mxm);
+      const int ciy = tile_y0 + ((cell - (tile << cells_log2)) >> tl.tlx);
       const int s = __shfl_sync(SKB_FULL, my_start, cj);
       const int n = GAP_CNT(cj);
       gap_cp_wait_one();
@@ -345,10 +350,17 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
               atomicOr(q.counts + 3, 2);
             }
           } else {
-            const int dk = cell_key(x, y, q.key);
-            stay = dk == cell;
+            // cell_key() == cell, spelled out on the cell coordinates (cheaper than
+            // the tile-major key itself; phase B / skb_gap_insert compute that)
+            double xs = x + q.key.offx, ys = y + q.key.offy;
+            if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+            const int ix = min(max((int)xs, 0), q.key.mx - 1);
+            const int iy = min(max((int)ys, 0), q.key.myp - 1);
+            stay = ix == cix && iy == ciy;
             mover = !stay;
-            local = mover && (unsigned)(dk - c0) < (unsigned)cpp;
+            const int loc = (((iy - tile_y0) << tl.tlx) | (ix - tile_x0)) - part_off;
+            local = mover && (unsigned)(ix - tile_x0) <= (unsigned)mxm &&
+                    (unsigned)(iy - tile_y0) <= (unsigned)mym && (unsigned)loc < (unsigned)cpp;
           }
         }
         // movers inside this CTA's cell range: scratch block

@@ -102,15 +102,53 @@ def reference_arm(a):
 
 # ----------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region: an NVML
+    polling thread (5 ms period; nvidia-smi -lms needs ~100 ms to deliver its first
+    line, longer than the timed region of a multi-GPU run), nvidia-smi as fall-back."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40,
+                "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.pw.append(nv.nvmlDeviceGetPowerUsage(h)/1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.005):
+                return
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML wants the physical one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -120,31 +158,36 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        if self.proc is None:
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+        else:
+            self.proc.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+                out, _ = self.proc.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+                out, _ = self.proc.communicate()
+            for ln in out.splitlines():
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    self.sm.append(float(f[1])); self.mx.append(float(f[2]))
+                    self.pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(self.NAMES, f[4:8]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+        sm, mx, pw = self.sm, self.mx, self.pw
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(self.reasons),
+                "source": "nvml" if self.thread is not None else "nvidia-smi"}
 
 
 def measured_peak():

@@ -141,15 +141,17 @@ gap_route_kernel(const double *__restrict__ lo, int cap, int n, double e0, doubl
 // One slot claim per warp and destination cell (rows arrive roughly ordered by source
 // tile, so a warp sees few distinct cells and its writes into one cell are contiguous).
 #define GAP_INS_ITEMS 4
-__global__ void __launch_bounds__(256)
-gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
-                  const int *__restrict__ gap_start, int *gap_count, KeyParams kp,
-                  double *leftover, int leftover_cap, int *counts) {
-  // GAP_INS_ITEMS independent rows per thread: the row load -> slot claim -> store
-  // chains overlap instead of adding up
+// Insert rows i0 + t*256 (t < GAP_INS_ITEMS, < n) into their cells; a warp-collective:
+// all 32 lanes of a warp call it together.  GAP_INS_ITEMS independent rows per thread:
+// the row load -> slot claim -> store chains overlap instead of adding up.
+__device__ __forceinline__ void gap_insert_rows(const double *__restrict__ rows, int n, int i0,
+                                                skb_particles_t P,
+                                                const int *__restrict__ gap_start,
+                                                int *gap_count, const KeyParams &kp,
+                                                double *leftover, int leftover_cap,
+                                                int *counts) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int i0 = blockIdx.x * (256 * GAP_INS_ITEMS) + threadIdx.x;
   double r0[GAP_INS_ITEMS], r1[GAP_INS_ITEMS], r2[GAP_INS_ITEMS], r3[GAP_INS_ITEMS],
       r4[GAP_INS_ITEMS];
   bool valid[GAP_INS_ITEMS];
@@ -200,6 +202,14 @@ gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
+                  const int *__restrict__ gap_start, int *gap_count, KeyParams kp,
+                  double *leftover, int leftover_cap, int *counts) {
+  gap_insert_rows(rows, n, blockIdx.x * (256 * GAP_INS_ITEMS) + threadIdx.x, P, gap_start,
+                  gap_count, kp, leftover, leftover_cap, counts);
 }
 
 // ---- push on the gapped layout -----------------------------------------------------------
@@ -431,43 +441,9 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   if (scr_rows > 0) {
     const int nrows = min(s_nrows, scr_rows);
     if (threadIdx.x == 0 && nrows) atomicAdd(q.counts + 4, nrows);   // statistics
-    for (int r0 = (int)(threadIdx.x & ~31); r0 < nrows; r0 += GAP_THREADS) {
-      const int r = r0 + lane;
-      const bool valid = r < nrows;
-      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
-      if (valid) {
-        const double *o = scr + (size_t)r * 5;
-        x = o[0]; y = o[1]; vx = o[2]; vy = o[3]; vz = o[4];
-      }
-      const int key = valid ? cell_key(x, y, q.key) : -1 - lane;
-      const unsigned peers = __match_any_sync(SKB_FULL, key);
-      const int leader = __ffs(peers) - 1, cnt = __popc(peers);
-      int s = 0, cap = 0, base = 0;
-      if (valid && lane == leader) {
-        base = atomicAdd(q.gap_count + key, cnt);
-        s = q.gap_start[key]; cap = q.gap_start[key + 1] - s;
-        const int over = min(max(base + cnt - cap, 0), cnt);
-        if (over) atomicSub(q.gap_count + key, over);
-      }
-      s = __shfl_sync(SKB_FULL, s, leader);
-      cap = __shfl_sync(SKB_FULL, cap, leader);
-      const int slot = __shfl_sync(SKB_FULL, base, leader) + __popc(peers & lt);
-      if (valid) {
-        if (slot < cap) {
-          const long long d = (long long)s + slot;
-          P.x[d] = x; P.y[d] = y; P.vx[d] = vx; P.vy[d] = vy; P.vz[d] = vz;
-        } else {
-          const int l = atomicAdd(q.lcounts + 0, 1);
-          if (l < q.leftover_cap) {
-            const size_t lc = (size_t)q.leftover_cap;
-            q.leftover[l] = x; q.leftover[lc + l] = y; q.leftover[2 * lc + l] = vx;
-            q.leftover[3 * lc + l] = vy; q.leftover[4 * lc + l] = vz;
-          } else {
-            q.lcounts[1] = 1;
-          }
-        }
-      }
-    }
+    for (int r0 = 0; r0 < nrows; r0 += GAP_THREADS * GAP_INS_ITEMS)
+      gap_insert_rows(scr, nrows, r0 + (int)threadIdx.x, P, q.gap_start, q.gap_count, q.key,
+                      q.leftover, q.leftover_cap, q.lcounts);
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(q.pool_owner + s_blk, 0);
   }

@@ -42,6 +42,7 @@ class InitialCondition:
         gen = torch.Generator(device=ions.device)
         gen.manual_seed((self.seed if self.seed is not None else 0) + manifold.comm.rank)
         kw = dict(generator=gen, device=ions.device, dtype=torch.float64)
+        ions._rep = "dense"           # (whatever was stored before is discarded)
         d = ions._data
         d[0, :N] = torch.rand(N, **kw)*manifold.nx
         d[1, :N] = torch.rand(N, **kw)*manifold.nyp + manifold.edges[0]

@@ -168,6 +168,8 @@ class Particles:
 
     @N.setter
     def N(self, n):
+        if getattr(self, "_rep", "dense") == "gapped":
+            self._dense()              # "the first N entries" only means something there
         self._N = int(n)
         self._N_global = None          # unknown until the next reduction
 

@@ -1,6 +1,7 @@
 """One small invocation of the hot path on cuda:0, checked against the CPU oracle:
-push (CIC) + boundary epilogue + migration + tile sort + deposit + guards on a
-32x32 grid with 16 particles per cell."""
+push (CIC) + boundary epilogue + migration + ordering + deposit + guards on a
+32x32 grid with 16 particles per cell, once on the dense layout (tile sort) and once
+on the gapped layout (per-cell slot ranges)."""
 import numpy as np
 
 
@@ -18,23 +19,30 @@ def run():
     x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
     vx, vy, vz = rng.normal(0, 0.3, (3, n))
 
-    m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
-    ions = sk.Particles(m, int(1.5*n), charge=1.0, mass=1.0, order=1)
-    ions.initialize(x, y, vx, vy, vz)
-    E = sk.Field(m, dtype=sk.Float3)
-    B = sk.Field(m, dtype=sk.Float3)
-    xg, yg = np.meshgrid(m.x, m.y)
-    E['x'].active = 0.1*np.sin(2*np.pi*xg)
-    E['y'].active = 0.1*np.cos(2*np.pi*yg)
-    B['z'].active = 1.0 + 0.1*np.sin(2*np.pi*(xg + yg))
-    E.copy_guards()
-    B.copy_guards()
-    src = sk.Sources(m)
+    def on_gpu(gapped):
+        m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
+        ions = sk.Particles(m, int((4.0 if gapped else 1.5)*n), charge=1.0, mass=1.0,
+                            order=1)
+        ions.gapped = gapped
+        ions.initialize(x, y, vx, vy, vz)
+        E = sk.Field(m, dtype=sk.Float3)
+        B = sk.Field(m, dtype=sk.Float3)
+        xg, yg = np.meshgrid(m.x, m.y)
+        E['x'].active = 0.1*np.sin(2*np.pi*xg)
+        E['y'].active = 0.1*np.cos(2*np.pi*yg)
+        B['z'].active = 1.0 + 0.1*np.sin(2*np.pi*(xg + yg))
+        E.copy_guards()
+        B.copy_guards()
+        src = sk.Sources(m)
+        for it in range(3):
+            ions.push(E, B, 0.5*m.dx)
+        assert ions._rep == ("gapped" if gapped else "dense")
+        src.deposit(ions, set_boundaries=True)
+        torch.cuda.synchronize()
+        return m, ions, src, E, B
+
+    m, ions, src, E, B = on_gpu(False)
     dt = 0.5*m.dx
-    for it in range(3):
-        ions.push(E, B, dt)
-    src.deposit(ions, set_boundaries=True)
-    torch.cuda.synchronize()
 
     # the same on the CPU oracle
     g = orc.Grid(nx, ny, lbx=2, lby=2)
@@ -56,11 +64,15 @@ def run():
     def rows(a):
         a = np.ascontiguousarray(a).view(np.float64).reshape(-1, 5)
         return a[np.lexsort(a.T[::-1])]
-    assert ions.N == N[0]
-    got, exp = rows(np.asarray(ions[:ions.N])), rows(parts[0][:N[0]])
-    assert np.array_equal(got, exp), "particles differ from the oracle"
-    a = np.asarray(src).view(np.float64)
-    b = so.view(np.float64)
-    err = np.abs(a - b).max()/np.abs(b).max()
-    assert err < 1e-12, "sources differ from the oracle: %g" % err
-    print("smoke OK: %d particles bit-exact, sources rel err %.2e" % (ions.N, err))
+    for layout in ("dense", "gapped"):
+        if layout == "gapped":
+            m, ions, src, E, B = on_gpu(True)
+        assert ions.N == N[0]
+        got, exp = rows(np.asarray(ions[:ions.N])), rows(parts[0][:N[0]])
+        assert np.array_equal(got, exp), "particles differ from the oracle (%s)" % layout
+        a = np.asarray(src).view(np.float64)
+        b = so.view(np.float64)
+        err = np.abs(a - b).max()/np.abs(b).max()
+        assert err < 1e-12, "sources differ from the oracle (%s): %g" % (layout, err)
+        print("smoke OK (%s layout): %d particles bit-exact, sources rel err %.2e" % (
+            layout, ions.N, err))

@@ -6,12 +6,17 @@
 // them).  The push then
 //   * writes the particles that stay in their cell back into the same range, compacted
 //     to the front (it has to write them anyway: 80 B/particle, as before),
-//   * appends the few that change cell to a mover list (AoS rows) and the ones that
-//     leave the slab to the exchange buffers (cppmove2's pack, pplib2.c:666-707),
-// and a small insertion kernel drops movers and arrivals into the free slots of their
-// new cells.  No histogram, no scan, no move pass: ~100 B/particle for push + ordering
-// instead of 160 B.  When a cell's slack or the mover list overflows, nothing is lost:
-// the particle stays where it is (or in the leftover list), a flag is raised and the
+//   * packs the ones that leave the slab into the exchange buffers (cppmove2's pack,
+//     pplib2.c:666-707),
+//   * parks the ones that move to another cell of the same thread block in a scratch
+//     block (L2 resident) and, once all cells of the block are compacted, drops them
+//     into the free slots of their new cells itself,
+//   * appends the rest (they cross a block boundary) to a global mover list (AoS rows)
+// and a small insertion kernel drops those and the arrivals into their new cells.  No
+// histogram, no scan, no move pass: ~100 B/particle for push + ordering instead of
+// 176 B.  When a cell's slack or the mover list overflows, nothing is lost: the
+// particle goes to a small leftover list (pushed / deposited by the generic kernels,
+// re-inserted every step) or stays parked in its old cell with a flag raised, and the
 // caller rebuilds the layout through the dense path (densify -> tile sort -> build).
 //
 // New component (no reference counterpart); ordering stays a performance property.
@@ -20,14 +25,10 @@
 #include "gather.cuh"
 
 #define GAP_THREADS 256
-#ifndef GAP_UNR
-#define GAP_UNR 2
-#endif
 #ifndef GAP_MINB
-#define GAP_MINB 3
+#define GAP_MINB 3        // resident CTAs/SM aimed at for CIC (80 registers, no spills)
 #endif
-
-#define GAP_BLOCK 64
+#define GAP_BLOCK 64      // particles per ring stage
 __device__ __forceinline__ void gap_cp_async16(double *smem_dst, const double *gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -35,12 +36,9 @@ __device__ __forceinline__ void gap_cp_async16(double *smem_dst, const double *g
 __device__ __forceinline__ void gap_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gap_cp_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void gap_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void gap_prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 // ---- build / densify ----------------------------------------------------------------
-// capacity of a cell with n particles: n + max(16, n/4), rounded up to 16 slots (128 B)
+// capacity of a cell with n particles: 25 % slack, rounded up
 __global__ void __launch_bounds__(256)
 gap_caps_kernel(const int *__restrict__ cell_end, int ncells, int *gap_start) {
   int c = blockIdx.x * 256 + threadIdx.x;

@@ -12,6 +12,10 @@ Every method that changes positions ends with the tile sort (skb_tile_sort), so
 push gathers from shared-memory field tiles and deposit accumulates runs of
 same-cell particles in registers.  The ordering is a performance property only:
 kernels are correct for any order (user code may overwrite coordinates at will).
+
+With `gapped = True` the particles live in per-cell slot ranges between push calls
+(skb_push_gapped keeps them ordered without a move pass); every other method and every
+NumPy-style access first converts back to the dense arrays described above.
 """
 import ctypes as C
 import os

@@ -404,9 +404,11 @@ def b200_arm(a):
     standalone = summarize(acc2)
     if accg and all(accg.values()):
         standalone.update({"dense_" + k: v for k, v in summarize(acc).items()})
-        # in-place movers are read and written twice: + 80 B each
-        alg["push"] = 80.0*npart + 80.0*nlocal + 48.0*cells
+        # the push is rated at 80 B/particle (+ E,B tiles) although this
+        # kernel also maintains the ordering (block-local movers are written, read back
+        # and written again: + 80 B each, reported separately)
         kern = summarize(accg)
+        kern["push"]["bytes_incl_reinsertion"] = 80.0*npart + 80.0*nlocal + 48.0*cells
         candidates, tkey = ("push", "deposit"), {"push": "push_gapped"}
     else:
         kern = summarize(acc)
@@ -415,11 +417,15 @@ def b200_arm(a):
     for v in kern.values():
         v["share"] = round(v["ms"]/step_ms, 4)
     dom = max(candidates, key=lambda k: kern[k]["ms"])
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"],
+    roofline = {"kernel": tkey.get(dom, dom), "bound": "hbm",
+                "achieved": kern[dom]["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": kern[dom]["alg_bytes"],
-                "ms_per_launch": kern[dom]["ms"]}
+                "ms_per_launch": kern[dom]["ms"],
+                # whole step against its 120 algorithmic bytes per particle-step
+                # (ordering, migration and halo traffic are overhead)
+                "step_frac": round(120.0*npart/(ms/a.steps*1e-3)/1e9/peak, 4)}
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
         try:

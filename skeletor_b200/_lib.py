@@ -143,11 +143,25 @@ def load():
     return lib
 
 
+# measurement hook (bench.py): {entry point name: [(start event, end event), ...]};
+# when set, the named calls are bracketed by CUDA events on the current stream
+trace = None
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point, raising on a CUDA error."""
     global launches, kernel_launches
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if trace is not None and name in trace:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        trace[name].append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     launches += 1
     kernel_launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:

@@ -38,6 +38,8 @@ class Sources(Field):
             self.t.zero_()
         # Rate of shear
         S = getattr(self.grid, 'S', 0.0)
+        if particles.deterministic:
+            particles._dense()         # the fixed-order deposit needs the dense ordering
         particles._ensure_sorted()
         if particles.deterministic and particles._sorted and particles.N > 0:
             _lib.call("skb_deposit_deterministic", particles._c, particles.N, self.ptr,

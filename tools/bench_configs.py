@@ -14,10 +14,12 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def uniform_plasma(sk, torch, m, ppc, order, seed=1234):
+def uniform_plasma(sk, torch, m, ppc, order, seed=1234, gapped=False):
     n = m.nx*m.nyp*ppc
-    ions = sk.Particles(m, int(1.05*n) + 4096, charge=1.0, mass=1.0, order=order,
+    nmax = int((1.36 if gapped else 1.05)*n) + 4096
+    ions = sk.Particles(m, nmax + (nmax & 1), charge=1.0, mass=1.0, order=order,
                         nbmax=max(n//100, 1 << 16))
+    ions.gapped = gapped
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     d = ions._data
@@ -45,7 +47,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="scale grid edge (testing)")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--layout", default="gapped", choices=["gapped", "dense"],
+                    help="particle layout for the push + deposit loops (configs 2, 4); "
+                         "the time steppers (config 3) run on the dense layout")
     a = ap.parse_args()
+    gapped = a.layout == "gapped"
     import torch
     import skeletor_b200 as sk
     from skeletor_b200.time_steppers.horowitz import TimeStepper as Horowitz
@@ -57,7 +63,7 @@ def main():
     # config 2: Landau/ion-acoustic loop, 1024^2 x 64 ppc, CIC, Ohm included
     nx = sc(1024)
     m = sk.Manifold(nx, nx, comm, Lx=1.0, Ly=1.0)
-    ions, n = uniform_plasma(sk, torch, m, 64, 1)
+    ions, n = uniform_plasma(sk, torch, m, 64, 1, gapped=gapped)
     dt = 0.1*m.dx
     E = sk.Field(m, dtype=sk.Float3); E.copy_guards()
     B = sk.Field(m, dtype=sk.Float3); B.copy_guards()
@@ -74,7 +80,8 @@ def main():
     src.deposit(ions, set_boundaries=True)
     ms = timed(torch, step2, a.steps)
     out["config2_landau_loop"] = {"grid": [nx, nx], "ppc": 64, "particles": n,
-                                  "ms_per_step": ms, "particle_steps_per_s": n/ms*1e3}
+                                  "ms_per_step": ms, "particle_steps_per_s": n/ms*1e3,
+                                  "layout": ions._rep}
     del ions, E, B, src
     torch.cuda.empty_cache()
 
@@ -119,7 +126,7 @@ def main():
 
     # config 4: shearing sheet, push_modified + sheared guards, 2048^2 x 64 ppc
     m = sk.ShearingManifold(nx, nx, comm, lbx=2, lby=2, S=-1.5, Omega=1.0, Lx=1.0, Ly=1.0)
-    ions, n = uniform_plasma(sk, torch, m, 64, 1)
+    ions, n = uniform_plasma(sk, torch, m, 64, 1, gapped=gapped)
     ions._data[2:5, :n] *= 0.05
     E = sk.Field(m, dtype=sk.Float3); E.copy_guards()
     B = sk.Field(m, dtype=sk.Float3); B.copy_guards()
@@ -136,7 +143,8 @@ def main():
         src.copy_guards()
     ms = timed(torch, step4, a.steps)
     out["config4_shearing_sheet"] = {"grid": [nx, nx], "ppc": 64, "particles": n,
-                                     "ms_per_step": ms, "particle_steps_per_s": n/ms*1e3}
+                                     "ms_per_step": ms, "particle_steps_per_s": n/ms*1e3,
+                                     "layout": ions._rep}
     print(json.dumps(out))
 
 

@@ -291,6 +291,22 @@ int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
                     int nbmax, int *counts, int rank, int nvp, double *leftover,
                     int leftover_cap, int nleft, int *leftover_counts, double *scratch,
                     int scratch_rows, int npool, int *pool_owner, void *stream);
+/* push_and_deposit_cic/tsc (push_and_deposit.pyx:10,91) on the gapped layout: update != 0
+ * does what skb_push_gapped does after the half-step deposit (second half drift, x wrap,
+ * routing; counts / leftover as there), update == 0 only deposits (predictor sweep,
+ * nothing is written).  counts[3] bit 4 (and ihole[0] == -1 for a leftover particle;
+ * ihole: >= nleft + 1 ints of scratch) flags a particle that moved more than half a cell
+ * in the half step (:66-68). */
+int skb_push_and_deposit_gapped(skb_particles_t p, const double *E, const double *B,
+                                const skb_grid_t *grid, int order, double qtmh, double dt,
+                                double *current, double S, int update, int *ihole,
+                                int ntmax, int tlx, int tly, const int *gap_start,
+                                int *gap_count, double *movers, int mover_cap,
+                                double *sbufl, double *sbufr, int nbmax, int *counts,
+                                int rank, int nvp, double *leftover, int leftover_cap,
+                                int nleft, int *leftover_counts, double *scratch,
+                                int scratch_rows, int npool, int *pool_owner,
+                                void *stream);
 int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
                    int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
                    double *leftover, int leftover_cap, int *counts, void *stream);

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "gather.cuh"
+#include "deposit.cuh"
 
 #define GAP_THREADS 256
 #ifndef GAP_MINB
@@ -236,14 +237,31 @@ struct GapPush {
   int *lcounts;              // [0] leftover rows, [1] leftover overflow
 };
 
-template <int ORDER, bool MODIFIED>
-__global__ void __launch_bounds__(GAP_THREADS, (ORDER == 1) ? GAP_MINB : 2)
+// fused push_and_deposit on the gapped layout (push_and_deposit.pyx:10-170): sources
+// grid, deposit offsets / shear, half-step drift factors
+struct GapDeposit {
+  double *cur;
+  DepParams dp;
+  double d2x, d2y;           // 0.5*dt/dx, 0.5*dt/dy, push_and_deposit.pyx:37-38
+};
+
+// PD = 0: push (push / push_modified + boundary epilogue)
+// PD = 1: push_and_deposit, update = True   (gather at the old position, kick, half
+//         drift, deposit, second half drift, x wrap, then the same routing as PD = 0)
+// PD = 2: push_and_deposit, update = False  (deposit only: nothing is written back)
+template <int ORDER, bool MODIFIED, int PD>
+__global__ void __launch_bounds__(GAP_THREADS, (ORDER == 1 && PD == 0) ? GAP_MINB
+                                               : (ORDER == 2 && PD != 0) ? 1 : 2)
 push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
                    const double *__restrict__ B, DevGrid g, DevTiling tl, GapPush q,
-                   int parts, int wstride, int wrows) {
+                   GapDeposit dq, int parts, int wstride, int wrows) {
+  constexpr int NS = ORDER + 1;
   extern __shared__ double smem[];
   double *sE = smem;
   double *sB = smem + (size_t)wstride * wrows * 3;
+  // (PD) window of the sources grid, behind the E, B windows and the particle rings
+  double *sw = sB + (size_t)wstride * wrows * 3 + (GAP_THREADS / 32) * (2 * 5 * GAP_BLOCK);
+  if constexpr (PD != 0) zero_window(sw, wstride * wrows * 4);
   const int cells_log2 = tl.tlx + tl.tly;
   const int cpp = (1 << cells_log2) / parts;
   const int tile = blockIdx.x / parts;
@@ -314,12 +332,20 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
       gap_cp_commit();
     }
     int stage = 0, wcur = 0;                         // wcur: stayers written so far
+    Acc<NS> acc;                                     // (PD) stencil sums of the current cell
     while (cj < ncell) {
       const int cell = wc0 + cb + cj;
       const int cix = tile_x0 + ((cell - (tile << cells_log2)) & mxm);
       const int ciy = tile_y0 + ((cell - (tile << cells_log2)) >> tl.tlx);
       const int s = __shfl_sync(SKB_FULL, my_start, cj);
       const int n = GAP_CNT(cj);
+      if constexpr (PD != 0) {
+        if (cbase == 0) {                            // first block of a cell
+#pragma unroll
+          for (int i = 0; i < NS * NS * 4; i++) acc.v[i] = 0.0;
+          acc.ix = cix; acc.iy = ciy;
+        }
+      }
       gap_cp_wait_one();
       __syncwarp();
       const double *pb = ring + stage * (5 * GAP_BLOCK);
@@ -334,15 +360,39 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
           const double *pp = pb + u * 32 + lane;
           x = pp[0]; y = pp[GAP_BLOCK]; vx = pp[2 * GAP_BLOCK]; vy = pp[3 * GAP_BLOCK];
           vz = pp[4 * GAP_BLOCK];
-          fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
-          x = x + vx * q.dtdsx;                      // drift_particle, particle_push.pxd:88-91
-          y = y + vy * q.dtdsy;
-          if (q.flags & SKB_EPI_SHEAR) {             // particle_boundary.pyx:41-49
-            if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
-            if (y >= (double)g.ny) { x = x + q.x_boost; vx = vx + q.vx_boost; }
+          if constexpr (PD == 0) {
+            fields_and_kick<ORDER, MODIFIED>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
+            x = x + vx * q.dtdsx;                    // drift_particle, particle_push.pxd:88-91
+            y = y + vy * q.dtdsy;
+            if (q.flags & SKB_EPI_SHEAR) {           // particle_boundary.pyx:41-49
+              if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
+              if (y >= (double)g.ny) { x = x + q.x_boost; vx = vx + q.vx_boost; }
+            }
+            if (q.flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, nxd);
+          } else {
+            const double xold = x, yold = y;
+            fields_and_kick<ORDER, false>(sE, sB, w, wstride, E, B, g, q.k, x, y, vx, vy, vz);
+            x = x + vx * dq.d2x;                     // first half of the drift
+            y = y + vy * dq.d2y;
+            // more than half a cell in half a step: push_and_deposit.pyx:66-68
+            if (fabs(x - xold) > 0.5 || fabs(y - yold) > 0.5) atomicOr(q.counts + 3, 4);
+            double xs = x + dq.dp.offx, ys = y + dq.dp.offy;
+            if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+            int ix, iy;
+            double wx[NS], wy[NS];
+            particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+            const double vxr = vx + dq.dp.S * (y * g.dy + g.y0);
+            if (ix == acc.ix && iy == acc.iy) accumulate<ORDER>(acc, wx, wy, vxr, vy, vz);
+            else stray_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, sw, w, wstride, dq.cur, g);
+            if constexpr (PD == 1) {
+              x = x + vx * dq.d2x;                   // second half of the drift
+              y = y + vy * dq.d2y;
+              x = wrap_x(x, nxd);
+            }
           }
-          if (q.flags & SKB_EPI_PERIODIC_X) x = wrap_x(x, nxd);
-          if (y < g.e0 || y >= g.e1) {               // leaves the slab: cppmove2's pack
+          if constexpr (PD == 2) {
+            // predictor sweep: particles stay untouched
+          } else if (y < g.e0 || y >= g.e1) {        // leaves the slab: cppmove2's pack
             double *buf; int slot; double yy = y;
             if (yy < g.e0) {
               if (q.rank == 0) yy += (double)g.ny;
@@ -371,6 +421,7 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
                     (unsigned)(iy - tile_y0) <= (unsigned)mym && (unsigned)loc < (unsigned)cpp;
           }
         }
+        if constexpr (PD == 2) continue;
         // movers inside this CTA's cell range: scratch block
         const unsigned lm = __ballot_sync(SKB_FULL, local && scr_rows > 0);
         if (lm) {
@@ -420,9 +471,31 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
       __syncwarp();                                  // stage fully read: refill it
       int nj = cj, nbase = cbase;
       GAP_ADVANCE(nj, nbase);
-      if (nj != cj) {
-        if (lane == 0) q.gap_count[cell] = wcur;
-        wcur = 0;
+      if (nj != cj) {                                // the cell is finished
+        if constexpr (PD != 2) {
+          if (lane == 0) q.gap_count[cell] = wcur;
+          wcur = 0;
+        }
+        if constexpr (PD != 0) {
+          // one warp reduction and one emit per cell (see deposit_cells_kernel)
+          const int lo = (NS == 3) ? 1 : 0;
+          const bool in_window = (acc.ix - lo >= w.x0) && (acc.ix - lo + NS <= w.x1) &&
+                                 (acc.iy - lo >= w.y0) && (acc.iy - lo + NS <= w.y1);
+          if constexpr (NS == 2) {
+            warp_reduce_scatter<16>(acc.v, lane);
+            if (lane < 16)
+              emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sw, w,
+                           wstride, dq.cur, g);
+          } else {
+            warp_reduce_scatter<32>(acc.v, lane);
+            warp_reduce_scatter<4>(acc.v + 32, lane);
+            emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sw, w,
+                         wstride, dq.cur, g);
+            if (lane < 4)
+              emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sw,
+                           w, wstride, dq.cur, g);
+          }
+        }
       }
       cj = nj; cbase = nbase;
       if (fj < ncell) { GAP_FETCH(stage, fj, fbase); GAP_ADVANCE(fj, fbase); }
@@ -436,6 +509,7 @@ push_gapped_kernel(skb_particles_t P, const double *__restrict__ E,
   }
   // phase B: all cells of this CTA are compacted; drop the parked movers into them
   __syncthreads();
+  if constexpr (PD != 0) flush_window(sw, w, wstride, dq.cur, g);
   if (scr_rows > 0) {
     const int nrows = min(s_nrows, scr_rows);
     if (threadIdx.x == 0 && nrows) atomicAdd(q.counts + 4, nrows);   // statistics
@@ -518,16 +592,16 @@ extern "C" int skb_gap_insert(const double *rows, int n, skb_particles_t p,
   return 0;
 }
 
-extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
-                               const skb_grid_t *grid, int order, double qtmh, double dt,
-                               int modified, double Omega, double S, int epi_flags,
-                               double epi_S, double epi_t, int tlx, int tly,
-                               const int *gap_start, int *gap_count, double *movers,
-                               int mover_cap, double *sbufl, double *sbufr, int nbmax,
-                               int *counts, int rank, int nvp, double *leftover,
-                               int leftover_cap, int nleft, int *leftover_counts,
-                               double *scratch, int scratch_rows, int npool,
-                               int *pool_owner, void *stream) {
+// pd: 0 = push, 1 = push_and_deposit with update, 2 = push_and_deposit without update
+static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double *B,
+                        const skb_grid_t *grid, int order, double qtmh, double dt,
+                        int modified, double Omega, double S, int epi_flags, double epi_S,
+                        double epi_t, double *current, double dep_S, int *ihole, int ntmax,
+                        int tlx, int tly, const int *gap_start, int *gap_count,
+                        double *movers, int mover_cap, double *sbufl, double *sbufr,
+                        int nbmax, int *counts, int rank, int nvp, double *leftover,
+                        int leftover_cap, int nleft, int *leftover_counts, double *scratch,
+                        int scratch_rows, int npool, int *pool_owner, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
   DevGrid g = make_grid(grid);
@@ -547,9 +621,16 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
   q.sbufl = sbufl; q.sbufr = sbufr; q.nbmax = nbmax; q.rank = rank; q.nvp = nvp;
   q.counts = counts;
   q.scratch = scratch; q.scratch_rows = scratch_rows;
-  q.npool = (scratch && pool_owner && scratch_rows > 0) ? npool : 0;
+  q.npool = (pd != 2 && scratch && pool_owner && scratch_rows > 0) ? npool : 0;
   q.pool_owner = pool_owner; q.gap_start = gap_start;
   q.leftover = leftover; q.leftover_cap = leftover_cap; q.lcounts = leftover_counts;
+  GapDeposit dq = {};
+  dq.cur = current;
+  dq.dp.offx = q.k.offEx;                          // offsetE reused, push_and_deposit.pyx:71
+  dq.dp.offy = q.k.offEy;
+  dq.dp.S = dep_S;
+  dq.d2x = 0.5 * dt / g.dx;
+  dq.d2y = 0.5 * dt / g.dy;
   // more blocks than CTAs can ever be resident, or the claim loop could spin forever
   if (q.npool > 0 && q.npool < 148 * 4) return (int)cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), st);
@@ -568,45 +649,97 @@ extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double 
     if (pv >= 1 && pv <= cells / 8 && (pv & (pv - 1)) == 0) parts = pv;
   }
   const int ws = window_stride(tl), wr = window_rows(tl);
-  // E and B windows + the warps' particle rings
-  const size_t smem = ((size_t)ws * wr * 3 * 2 + (GAP_THREADS / 32) * 2 * 5 * GAP_BLOCK) *
-                      sizeof(double);
+  // E and B windows + the warps' particle rings (+ the window of the sources grid)
+  const size_t smem = ((size_t)ws * wr * (3 * 2 + (pd ? 4 : 0)) +
+                       (GAP_THREADS / 32) * 2 * 5 * GAP_BLOCK) * sizeof(double);
   // 16-byte cp.async: the five arrays must be 16-byte aligned (and every gap_start even,
   // as skb_gap_build guarantees)
   if ((((uintptr_t)p.x | (uintptr_t)p.y | (uintptr_t)p.vx | (uintptr_t)p.vy |
         (uintptr_t)p.vz) & 15) != 0)
     return (int)cudaErrorMisalignedAddress;
   void (*k)(skb_particles_t, const double *, const double *, DevGrid, DevTiling, GapPush,
-            int, int, int);
-  if (order == 1) k = modified ? push_gapped_kernel<1, true> : push_gapped_kernel<1, false>;
-  else k = modified ? push_gapped_kernel<2, true> : push_gapped_kernel<2, false>;
+            GapDeposit, int, int, int);
+  if (pd == 0) {
+    if (order == 1) k = modified ? push_gapped_kernel<1, true, 0> : push_gapped_kernel<1, false, 0>;
+    else k = modified ? push_gapped_kernel<2, true, 0> : push_gapped_kernel<2, false, 0>;
+  } else if (pd == 1) {
+    k = order == 1 ? push_gapped_kernel<1, false, 1> : push_gapped_kernel<2, false, 1>;
+  } else {
+    k = order == 1 ? push_gapped_kernel<1, false, 2> : push_gapped_kernel<2, false, 2>;
+  }
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
+  if (pd) {                // in-band flag of the generic kernel below (ihole[0] = -1)
+    e = cudaMemsetAsync(ihole, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (nleft > 0) {
-    // the particles that found no slot last step: generic push in place, then onto the
-    // head of the mover list (or out to the neighbours) like everybody else
+    // the particles that found no slot last step: generic kernel in place, then onto
+    // the head of the mover list (or out to the neighbours) like everybody else
     if (nleft > leftover_cap || nleft > mover_cap) return (int)cudaErrorInvalidValue;
     const size_t lc = (size_t)leftover_cap;
     skb_particles_t lp = {leftover, leftover + lc, leftover + 2 * lc, leftover + 3 * lc,
                           leftover + 4 * lc};
-    skb_epilogue_t ep = {};
-    ep.flags = epi_flags & (SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X);
-    ep.S = epi_S; ep.t = epi_t;
-    int rc = skb_boris_push(lp, nleft, E, B, grid, order, qtmh, dt, modified, Omega, S,
-                            nullptr, &ep, stream);
+    int rc;
+    if (pd) {
+      if (nleft > ntmax) return (int)cudaErrorInvalidValue;
+      rc = skb_push_and_deposit(lp, nleft, E, B, grid, order, qtmh, dt, ihole, ntmax, current,
+                                dep_S, pd == 1, nullptr, nullptr, tlx, tly, stream);
+    } else {
+      skb_epilogue_t ep = {};
+      ep.flags = epi_flags & (SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X);
+      ep.S = epi_S; ep.t = epi_t;
+      rc = skb_boris_push(lp, nleft, E, B, grid, order, qtmh, dt, modified, Omega, S, nullptr,
+                          &ep, stream);
+    }
     if (rc) return rc;
-    gap_route_kernel<<<(nleft + 255) / 256, 256, 0, st>>>(
-        leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
-        sbufr, nbmax, counts);
-    SKB_CHECK_LAUNCH();
+    if (pd != 2) {
+      gap_route_kernel<<<(nleft + 255) / 256, 256, 0, st>>>(
+          leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
+          sbufr, nbmax, counts);
+      SKB_CHECK_LAUNCH();
+    }
   }
-  // the old leftovers are consumed: the list restarts (this kernel and the
-  // skb_gap_insert calls that follow append to it)
-  e = cudaMemsetAsync(leftover_counts, 0, 2 * sizeof(int), st);
-  if (e != cudaSuccess) return (int)e;
-  k<<<ntiles * parts, GAP_THREADS, smem, st>>>(p, E, B, g, tl, q, parts, ws, wr);
+  if (pd != 2) {
+    // the old leftovers are consumed: the list restarts (this kernel and the
+    // skb_gap_insert calls that follow append to it)
+    e = cudaMemsetAsync(leftover_counts, 0, 2 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k<<<ntiles * parts, GAP_THREADS, smem, st>>>(p, E, B, g, tl, q, dq, parts, ws, wr);
   SKB_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int skb_push_gapped(skb_particles_t p, const double *E, const double *B,
+                               const skb_grid_t *grid, int order, double qtmh, double dt,
+                               int modified, double Omega, double S, int epi_flags,
+                               double epi_S, double epi_t, int tlx, int tly,
+                               const int *gap_start, int *gap_count, double *movers,
+                               int mover_cap, double *sbufl, double *sbufr, int nbmax,
+                               int *counts, int rank, int nvp, double *leftover,
+                               int leftover_cap, int nleft, int *leftover_counts,
+                               double *scratch, int scratch_rows, int npool,
+                               int *pool_owner, void *stream) {
+  return gapped_sweep(0, p, E, B, grid, order, qtmh, dt, modified, Omega, S, epi_flags, epi_S,
+                      epi_t, nullptr, 0.0, nullptr, 0, tlx, tly, gap_start, gap_count, movers,
+                      mover_cap, sbufl, sbufr, nbmax, counts, rank, nvp, leftover,
+                      leftover_cap, nleft, leftover_counts, scratch, scratch_rows, npool,
+                      pool_owner, stream);
+}
+
+extern "C" int skb_push_and_deposit_gapped(
+    skb_particles_t p, const double *E, const double *B, const skb_grid_t *grid, int order,
+    double qtmh, double dt, double *current, double S, int update, int *ihole, int ntmax,
+    int tlx, int tly, const int *gap_start, int *gap_count, double *movers, int mover_cap,
+    double *sbufl, double *sbufr, int nbmax, int *counts, int rank, int nvp, double *leftover,
+    int leftover_cap, int nleft, int *leftover_counts, double *scratch, int scratch_rows,
+    int npool, int *pool_owner, void *stream) {
+  return gapped_sweep(update ? 1 : 2, p, E, B, grid, order, qtmh, dt, 0, 0.0, 0.0,
+                      SKB_EPI_PERIODIC_X, 0.0, 0.0, current, S, ihole, ntmax, tlx, tly,
+                      gap_start, gap_count, movers, mover_cap, sbufl, sbufr, nbmax, counts,
+                      rank, nvp, leftover, leftover_cap, nleft, leftover_counts, scratch,
+                      scratch_rows, npool, pool_owner, stream);
 }

@@ -158,6 +158,7 @@ class Particles:
         # pass.  Needs Nmax >= ~1.3 N; push()/push_modified() fall back to the dense
         # path when the slot ranges do not fit.
         self.gapped = os.environ.get("SKELETOR_B200_GAPPED", "0") == "1"
+        self.gapped_push_and_deposit = True   # (only with gapped) fused sweep on that layout
         self.mover_fraction = 0.1     # size of the global mover list relative to Nmax
         self._rep = "dense"
         self._gap_start = None
@@ -403,10 +404,46 @@ class Particles:
                   self._pool_owner.data_ptr(), _stream())
         return cnt
 
-    def _gap_finish(self, cnt):
+    def _push_and_deposit_gapped(self, E, B, dt, update):
+        """push_and_deposit on the gapped layout (skb_push_and_deposit_gapped): the half-step
+        deposit is fused into the gapped push; update=False only deposits."""
+        m = self.manifold
+        comm = m.comm
+        self.time += dt
+        qtmh = self.charge/self.mass*dt/2
+        src = self.sources
+        src.t.zero_()
+        cnt = self._counts
+        had_leftovers = self._gap_nleft > 0
+        _lib.call("skb_push_and_deposit_gapped", self._c, E.ptr, B.ptr, m.c, self.order,
+                  float(qtmh), float(dt), src.ptr, 0.0, int(bool(update)),
+                  self.ihole.data_ptr(), self.ntmax - 1, TLX, TLY,
+                  self._gap_start.data_ptr(), self._gap_count.data_ptr(),
+                  self._movers.data_ptr(), self._movers.shape[0],
+                  self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
+                  cnt.data_ptr(), comm.rank, comm.size, self._leftover.data_ptr(),
+                  self._leftover.shape[1], self._gap_nleft, self._gcnt.data_ptr(),
+                  self._scratch.data_ptr(), self._scr_rows, self._npool,
+                  self._pool_owner.data_ptr(), _stream())
+        src.boundaries_set = False
+        src.normalize(self)
+        src.set_boundaries()
+        cfl = had_leftovers and int(self.ihole[0].item()) < 0
+        if update:
+            self._gap_finish(cnt, cfl)
+        elif cfl or (int(cnt[3].item()) & 4):
+            # moved more than half a cell in half a step (push_and_deposit.pyx:66-68): the
+            # reference's ihole[0] = -1, reported by particles.py:113-117
+            msg = "ihole overflow error: ntmax={}, ierr={}"
+            raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
+
+    def _gap_finish(self, cnt, cfl=False):
         m = self.manifold
         st = _stream()
         nm, nl, nr, fl, nlocal = cnt[:5].tolist()
+        if cfl or (fl & 4):
+            msg = "ihole overflow error: ntmax={}, ierr={}"
+            raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
         if fl & 2:
             raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
         nkeep = self._exchange(nl, nr)
@@ -725,6 +762,10 @@ class Particles:
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
+        if self.gapped and self.gapped_push_and_deposit and \
+                (self._rep == "gapped" or self._to_gapped()) and \
+                self._gap_nleft < self.ntmax - 1:
+            return self._push_and_deposit_gapped(E, B, dt, update)
         self._dense()
         self.time += dt
         qtmh = self.charge/self.mass*dt/2

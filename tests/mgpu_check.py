@@ -43,9 +43,9 @@ def main():
             super().__init__(manifold, 4*int(Nmax), **kw)
             self.gapped = True
 
-        def _gap_finish(self, cnt):
+        def _gap_finish(self, cnt, *args):
             pushes[0] += 1
-            return super()._gap_finish(cnt)
+            return super()._gap_finish(cnt, *args)
 
     ns = types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
@@ -57,7 +57,7 @@ def main():
              "sheared_tsc", "predictor_corrector_tsc", "horowitz_cic", "poisson"]
     lb = {"ionacoustic_cic": 1, "poisson": 1}
     if gapped:
-        names = names[:6]
+        names = names[:8]
     failed = 0
     for name in names:
         gold = np.load(os.path.join(HERE, "golden", name + ".npz"))

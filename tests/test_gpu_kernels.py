@@ -623,6 +623,68 @@ def test_gapped_layout_push_equals_oracle(order, shear, stress):
         assert nleft_max > 0            # some cells did run out of slots
 
 
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("stress", ["none", "cells"])
+def test_gapped_push_and_deposit_equals_oracle(order, stress):
+    """Particles.push_and_deposit on the gapped layout (skb_push_and_deposit_gapped), with
+    and without update, against the oracle's push_and_deposit + move + periodic_x: particles
+    bit-exact, half-step sources <= 1e-12; leftover particles (full cells) included"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 64, 32, 24
+    kw = dict(lbx=2, lby=2, Lx=2.0, Ly=1.0, x0=-1.0, y0=-0.5)
+    m = sk.Manifold(nx, ny, sk.COMM_SELF, **kw)
+    g = orc.Grid(nx, ny, **kw)
+    rng = np.random.default_rng(35)
+    n = nx*ny*npc
+    x = -1.0 + rng.uniform(0, 2.0, n)
+    y = -0.5 + rng.uniform(0, 1.0, n)
+    v = rng.normal(0, 0.6, (3, n))
+    if stress == "cells":
+        v = rng.normal(0, 0.4, (3, n))
+        v[0] += -2.5*x                                 # converging flow: cells fill up
+    E = random_field(g, orc.Float3, rng, -0.2, 0.2)
+    B = random_field(g, orc.Float3, rng)
+    dt = 0.2*g.dx
+    nmax = int(3.2*n)
+    ions = sk.Particles(m, nmax, charge=1.0, mass=1.5, order=order)
+    ions.gapped = True
+    ions.mover_fraction = 1.0
+    ions.initialize(x, y, v[0], v[1], v[2])
+    Ef, Bf = sk.Field(m, dtype=sk.Float3), sk.Field(m, dtype=sk.Float3)
+    Ef[...] = E
+    Bf[...] = B
+    p = np.zeros(nmax, orc.Particle)
+    p["x"][:n], p["y"][:n] = (x - g.x0)/g.dx, (y - g.y0)/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = v
+    parts, N = [p], [n]
+    qtmh = 1.0/1.5*dt/2
+    reps, nleft_max = [], 0
+    for it, update in enumerate([True, False, True, True, False, True, True, True]):
+        ions.push_and_deposit(Ef, Bf, dt, update)
+        reps.append(ions._rep)
+        nleft_max = max(nleft_max, ions._gap_nleft)
+        exp = g.field(orc.Float4)
+        ih = np.zeros(nmax + 1, np.int32)
+        orc.push_and_deposit(parts[0][:N[0]], E, B, g, order, qtmh, dt, ih, exp, 0.0, update)
+        assert ih[0] >= 0
+        # sources after normalize + add_guards + copy_guards, as Particles.push_and_deposit
+        so = exp
+        orc.normalize([so], [g], N, ions.charge, ions.n0)
+        orc.add_guards([so], [g])
+        orc.copy_guards([so], [g])
+        assert rel(np.asarray(ions.sources), so) < 1e-12
+        if update:
+            parts, N = orc.move(parts, N, [g])
+            orc.periodic_x(parts[0][:N[0]], g)
+        assert ions.N == N[0]
+        if it in (0, 3, 7):
+            assert np.array_equal(gu.sorted_rows(np.asarray(ions[:ions.N])),
+                                  gu.sorted_rows(parts[0][:N[0]]))
+    assert reps[0] == "gapped" and reps[1] == "gapped", reps
+    if stress == "cells":
+        assert nleft_max > 0
+
+
 def test_edge_positions_classify_exactly_like_the_reference():
     """particles sitting exactly on cell faces, slab edges and the periodic seam: the
     strict / non-strict comparisons and C truncation must match bit for bit"""

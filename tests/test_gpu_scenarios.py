@@ -33,9 +33,9 @@ def namespace(gapped=False):
             super().__init__(manifold, 4*int(Nmax), **kw)
             self.gapped = True
 
-        def _gap_finish(self, cnt):
+        def _gap_finish(self, cnt, *args):
             GAPPED_PUSHES[0] += 1
-            return super()._gap_finish(cnt)
+            return super()._gap_finish(cnt, *args)
 
     return types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
@@ -68,8 +68,7 @@ def test_scenario_matches_reference(name, layout, capsys):
     GAPPED_PUSHES[0] = 0
     res = sc.SCENARIOS[name](namespace(layout == "gapped"))
     assert set(res) == set(gold.files)
-    if layout == "gapped" and not name.startswith(("predictor", "horowitz")):
-        # (the time steppers only use push_and_deposit: dense path)
+    if layout == "gapped":
         assert GAPPED_PUSHES[0] > 0, "the gapped push never ran"
     # the steppers iterate Ohm/Faraday to convergence and amplify rounding a bit
     rtol = 1e-10 if ("horowitz" in name or "predictor" in name) else 1e-12

@@ -49,7 +49,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--layout", default="gapped", choices=["gapped", "dense"],
                     help="particle layout for the push + deposit loops (configs 2, 4); "
-                         "the time steppers (config 3) run on the dense layout")
+                         "and the push_and_deposit sweeps of the time steppers (config 3)")
     a = ap.parse_args()
     gapped = a.layout == "gapped"
     import torch
@@ -94,7 +94,7 @@ def main():
         m = sk.Manifold(nx, nx, comm, lbx=2, lby=2, Lx=0.5*nx, Ly=0.5*nx)
         # quiet start (11 x 11 sub-lattice = 121 ppc ~ the config's 128), cold-ish ions:
         # a noisy 128-ppc start drives O(1) electric fields through grad ln(rho)
-        ions, n = uniform_plasma(sk, torch, m, 121, 1)
+        ions, n = uniform_plasma(sk, torch, m, 121, 1, gapped=gapped)
         sq = 11
         ax = (torch.arange(nx*sq, device="cuda", dtype=torch.float64) + 0.5)/sq
         ions._data[0, :n] = ax.repeat(nx*sq)
@@ -118,7 +118,7 @@ def main():
             out[name] = {"grid": [nx, nx], "ppc": 121, "particles": n, "ms_per_iterate": ms,
                          "particle_sweeps_per_iterate": sweeps,
                          "particle_steps_per_s": sweeps*n/ms*1e3,
-                         "push_and_deposit_update_ms": t_pd}
+                         "push_and_deposit_update_ms": t_pd, "layout": ions._rep}
         except RuntimeError as err:
             out[name] = {"error": str(err)[:200]}
         del ions, B, e

@@ -19,6 +19,10 @@
 // re-inserted every step) or stays parked in its old cell with a flag raised, and the
 // caller rebuilds the layout through the dense path (densify -> tile sort -> build).
 //
+// The same kernel, instantiated with the half-step deposit of push_and_deposit
+// (push_and_deposit.pyx:10-170) between two half drifts, serves the time steppers
+// (skb_push_and_deposit_gapped).
+//
 // New component (no reference counterpart); ordering stays a performance property.
 #include <cstdlib>
 #include "common.cuh"

@@ -333,6 +333,8 @@ class Particles:
         Returns False (and stays dense) when the ranges do not fit in Nmax slots."""
         if self.N == 0 or not self.sort_enabled or self.deterministic:
             return False
+        if self.size % 2:
+            return False        # rows of the [5][Nmax] tensor must be 16-byte aligned
         if not (self._sorted and self._n_sorted == self.N):
             self.sort()
         self._gap_alloc()

@@ -60,6 +60,8 @@ def parse():
                     help="weak scaling: ny grows with the GPU count (ny rows PER GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the oracle parity checks after the timed region")
     return ap.parse_args()
 
 
@@ -200,6 +202,121 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ----------------------------------------------------------------------------------
+def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
+    """Parity at BENCH SCALE and at N ranks, through the public API, against the oracle
+    (checker only; runs after the timed region).
+
+    particles: a seeded sample of ~n_sample live particle rows per rank is pushed on the
+      host with oracle.push + periodic_y wrap + periodic_x (reference
+      particles.py:159-188: push, periodic_y, periodic_x); after ONE more ions.push on the
+      GPUs every expected row must be present, bit for bit and exactly once, in the union
+      of the ranks' live particles (the reference's own "N ranks == 1 rank" invariant,
+      tests/test_skeletor.py:142-150, at the benchmark's size).
+    sources: all particles whose stencil touches a band of `band` array rows (the top
+      rows of the slab incl. one guard row) are deposited with oracle.deposit
+      (deposit.pyx:6-34) and normalised (sources.py:52-63); compared with what
+      sources.deposit(ions) left in those rows (before the guard-cell fold), relative to
+      the band's maximum per component (<= 1e-12: summation order only) and, for rho,
+      also cell by cell.
+    """
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    m = ions.manifold
+    rank, size = comm.rank, comm.size
+    dev = ions.device
+    order = ions.order
+    og = orc.Grid(a.nx, a.ny, rank=rank, size=size, lbx=m.lbx, lby=m.lby, Lx=m.Lx, Ly=m.Ly)
+    Eh = np.ascontiguousarray(np.asarray(E)).view(orc.Float3).reshape(m.myp, m.mx)
+    Bh = np.ascontiguousarray(np.asarray(B)).view(orc.Float3).reshape(m.myp, m.mx)
+
+    # ---- expected particle rows ------------------------------------------------------
+    ions._dense()
+    N = int(ions.N)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + rank)
+    idx = torch.unique(torch.randint(0, N, (min(n_sample, N),), generator=gen, device=dev))
+    rows = ions._data[:, idx].t().contiguous().cpu().numpy()
+    part = np.ascontiguousarray(rows).view(orc.Particle).reshape(-1).copy()
+    qtmh = ions.charge/ions.mass*dt/2
+    orc.push(part, Eh, Bh, og, order, qtmh, dt)
+    # periodic_y: cppmove2 wraps on the edge ranks (pplib2.c:676-677, 692-693); with
+    # |vy dt/dy| << nyp nobody moves more than one slab, so only they can cross 0 / ny
+    y = part["y"]
+    lo, hi = y < 0.0, y >= float(a.ny)
+    y[lo] = y[lo] + float(a.ny)
+    y[hi] = y[hi] - float(a.ny)
+    orc.periodic_x(part, og)
+    exp_rows = np.ascontiguousarray(part).view(np.float64).reshape(-1, 5)
+    if size > 1:
+        exp_rows = np.concatenate(comm.allgather(exp_rows))
+
+    # ---- one more step on the GPUs -----------------------------------------------------
+    ions.push(E, B, dt)
+    src.deposit(ions)
+    src_raw = src.t.clone()             # normalised, guards not folded yet
+    src.add_guards()
+    src.copy_guards()
+
+    # ---- particles: every expected row present exactly once -------------------------
+    ions._dense()
+    N = int(ions.N)
+    M = exp_rows.shape[0]
+    exp = torch.as_tensor(exp_rows, device=dev)
+    ebits = exp.view(torch.int64)
+    sx, perm = torch.sort(ebits[:, 0].contiguous())
+    found = torch.zeros(M, dtype=torch.int64, device=dev)
+    lx = ions._data[0, :N].view(torch.int64)
+    CH = 1 << 26
+    for s0 in range(0, N, CH):
+        chunk = lx[s0:s0 + CH]
+        pos = torch.searchsorted(sx, chunk).clamp_(max=M - 1)
+        hit = (sx[pos] == chunk).nonzero().squeeze(1)
+        if hit.numel():
+            who = perm[pos[hit]]
+            cand = ions._data[:, s0 + hit].t().contiguous().view(torch.int64)
+            full = (cand == ebits[who]).all(dim=1)
+            found.index_add_(0, who[full], torch.ones_like(who[full]))
+        del pos, hit
+    if size > 1:
+        found = torch.as_tensor(comm.allreduce(found.cpu().numpy(), op=sk.comm.SUM))
+    n_once = int((found == 1).sum().item())
+    out = {"particles_sampled": int(M), "particles_found_once": n_once,
+           "particles_bitexact": n_once == M}
+
+    # ---- sources: band of rows vs oracle.deposit -----------------------------------
+    offy = (m.lby - 0.5) - m.noff + (0.5 if order == 2 else 0.0)
+    r1 = m.uby + 1                       # band = array rows [r0, r1): top rows + 1 guard row
+    r0 = r1 - band
+    lo_i, hi_i = r0 - 1, (r1 if order == 1 else r1 + 1)     # stencil-base rows that touch it
+    sel = []
+    for s0 in range(0, N, CH):
+        iy = (ions._data[1, s0:s0 + CH] + offy).to(torch.int32)
+        k = ((iy >= lo_i) & (iy < hi_i)).nonzero().squeeze(1)
+        if k.numel():
+            sel.append(ions._data[:, s0 + k].t().contiguous().cpu())
+        del iy, k
+    bp = torch.cat(sel).numpy() if sel else np.zeros((0, 5))
+    bpart = np.ascontiguousarray(bp).view(orc.Particle).reshape(-1).copy()
+    cur = og.field(orc.Float4)
+    orc.deposit(bpart, cur, og, order, float(getattr(m, "S", 0.0)))
+    fac = ions.charge*ions.n0*a.nx*a.ny/ions.N_global()
+    ref = np.ascontiguousarray(cur).view(np.float64).reshape(m.myp, m.mx, 4)[r0:r1]*fac
+    got = src_raw[r0:r1].cpu().numpy()
+    scale = np.abs(ref).reshape(-1, 4).max(axis=0)
+    rel = float((np.abs(got - ref).reshape(-1, 4).max(axis=0)/scale).max())
+    nz = ref[..., 0] != 0.0
+    rho_cell = float((np.abs(got[..., 0] - ref[..., 0])[nz]/np.abs(ref[..., 0][nz])).max())
+    if size > 1:
+        rel = comm.allreduce(rel, op=sk.comm.MAX)
+        rho_cell = comm.allreduce(rho_cell, op=sk.comm.MAX)
+    out.update({"sources_rel": rel, "sources_rho_cellwise_rel": rho_cell,
+                "sources_band": "array rows [uby+1-%d, uby+1) x all columns, %d particles "
+                                "per rank through oracle.deposit" % (band, bpart.shape[0])})
+    return out
+
+
 def b200_arm(a):
     import numpy as np
     import torch
@@ -280,7 +397,8 @@ def b200_arm(a):
     k0 = _lib.kernel_launches
     # CUDA events around the hot C-ABI calls of every timed step (no extra syncs): the
     # roofline below is the AVERAGE launch duration over the timed region
-    hot = ("skb_push_gapped", "skb_boris_push", "skb_tile_sort_precounted", "skb_deposit")
+    hot = ("skb_push_gapped", "skb_push_deposit_gapped", "skb_boris_push",
+           "skb_tile_sort_precounted", "skb_deposit")
     _lib.trace = {k: [] for k in hot}
     ms = timed(step, a.steps)
     live = {k: [e0.elapsed_time(e1) for e0, e1 in v] for k, v in _lib.trace.items() if v}
@@ -295,28 +413,47 @@ def b200_arm(a):
     # (g) gapped layout, the default step: push on per-cell slot ranges (movers parked
     #     and re-inserted by the kernel itself) | migration + insertion of the rest |
     #     deposit | guards
-    accg, nlocal = None, 0
+    accg, accu, nlocal = None, None, 0
+    fused = bool(gapped and ions._rep == "gapped" and
+                 (ions.fuse_deposit is True or
+                  (ions.fuse_deposit == "auto" and ions._fuse_next)))
+    pname = "push_deposit" if fused else "push"
     if gapped and ions._rep == "gapped":
-        accg = {"push": [], "migrate_insert": [], "deposit": [], "guards": []}
+        accg = {pname: [], "migrate_insert": [], "sources" if fused else "deposit": [],
+                "guards": []}
         for _ in range(3):
             if ions._rep != "gapped" and not ions._to_gapped():
                 break
             t = [ev() for _ in range(5)]
             torch.cuda.synchronize()
-            t[0].record(); cnt = ions._gap_kernel(E, B, dt, False)
-            t[1].record(); ions._gap_finish(cnt)
+            t[0].record(); cnt = ions._gap_kernel(E, B, dt, False, fused)
+            t[1].record(); ions._gap_finish(cnt, fused=fused)
             t[2].record()
-            src.t.zero_()
-            _lib.call("skb_deposit", ions._c, ions.N, src.ptr, m.c, ions.order, 0.0,
-                      ions._tiling_c(), torch.cuda.current_stream().cuda_stream)
+            src.deposit(ions)      # fused: copy of the push's grid + normalize
             t[3].record()
-            src.boundaries_set = False
-            src.normalize(ions); src.add_guards(); src.copy_guards()
+            src.add_guards(); src.copy_guards()
             t[4].record()
             torch.cuda.synchronize()
             nlocal = ions._gap_stats[6]
             for name, i in zip(accg, range(4)):
                 accg[name].append(t[i].elapsed_time(t[i + 1]))
+        # the two kernels on their own (what runs when the deposit does not follow a push)
+        accu = {"push_unfused": [], "deposit_unfused": []}
+        for _ in range(3):
+            if ions._rep != "gapped" and not ions._to_gapped():
+                break
+            t = [ev() for _ in range(4)]
+            torch.cuda.synchronize()
+            t[0].record(); cnt = ions._gap_kernel(E, B, dt, False, False)
+            t[1].record(); ions._gap_finish(cnt)
+            src.t.zero_()
+            t[2].record()
+            _lib.call("skb_deposit", ions._c, ions.N, src.ptr, m.c, ions.order, 0.0,
+                      ions._tiling_c(), torch.cuda.current_stream().cuda_stream)
+            t[3].record()
+            torch.cuda.synchronize()
+            accu["push_unfused"].append(t[0].elapsed_time(t[1]))
+            accu["deposit_unfused"].append(t[2].elapsed_time(t[3]))
         ions._dense()
     # (a) the step as it runs by default: push (+ fused boundary epilogue and sort
     #     histogram) | migration | precounted tile sort | deposit | guards
@@ -392,7 +529,12 @@ def b200_arm(a):
     # algorithmic bytes per launch: push 80 B/particle + E,B tiles
     # 48 B/cell; deposit 40 B/particle + 32 B/cell; precounted sort: 80 B (move), full
     # sort: + 16 B key pass; recompute passes: 40 B read / 40 B read + 40 B written
+    # fused push + deposit: SURVEY.md §8d's figure for a sweep that reads and writes every
+    # particle once (as push_and_deposit(update=True)): 80 B + E,B read and sources written
     alg = {"push": 80.0*npart + 48.0*cells, "deposit": 40.0*npart + 32.0*cells,
+           "push_deposit": 80.0*npart + 80.0*cells,
+           "push_unfused": 80.0*npart + 48.0*cells,
+           "deposit_unfused": 40.0*npart + 32.0*cells,
            "tile_sort": 80.0*npart, "push_plain": 80.0*npart + 48.0*cells,
            "tile_sort_full": 96.0*npart, "push_count": 40.0*npart + 48.0*cells,
            "push_scatter": 80.0*npart + 48.0*cells}
@@ -410,12 +552,17 @@ def b200_arm(a):
     standalone = summarize(acc2)
     if accg and all(accg.values()):
         standalone.update({"dense_" + k: v for k, v in summarize(acc).items()})
+        if accu and all(accu.values()):
+            standalone.update(summarize(accu))
         # the push is rated at 80 B/particle (+ E,B tiles) although this
         # kernel also maintains the ordering (block-local movers are written, read back
         # and written again: + 80 B each, reported separately)
         kern = summarize(accg)
-        kern["push"]["bytes_incl_reinsertion"] = 80.0*npart + 80.0*nlocal + 48.0*cells
-        candidates, tkey = ("push", "deposit"), {"push": "push_gapped"}
+        kern[pname]["bytes_incl_reinsertion"] = alg[pname] + 80.0*nlocal
+        candidates = (pname,) if fused else ("push", "deposit")
+        tkey = {"push": "push_gapped (cell_stream_kernel, PD=0)",
+                "push_deposit": "push_deposit_gapped (cell_stream_kernel, PD=3: push + "
+                                "full-step deposit in one sweep)"}
     else:
         kern = summarize(acc)
         candidates, tkey = ("push", "tile_sort", "deposit"), {}
@@ -427,6 +574,7 @@ def b200_arm(a):
     # launches the kernel (skb_deposit is also called for the handful of leftover
     # particles of the gapped layout: keep the big launches only)
     entry = {"push": "skb_push_gapped" if accg else "skb_boris_push",
+             "push_deposit": "skb_push_deposit_gapped",
              "tile_sort": "skb_tile_sort_precounted", "deposit": "skb_deposit"}
     for name, ep in entry.items():
         ts = [t for t in live.get(ep, []) if t > 0.2*max(live[ep])]
@@ -440,20 +588,46 @@ def b200_arm(a):
     else:
         dom_ms, how = kern[dom]["ms"], "instrumented pass after the timed region, best of 3"
     dom_gbs = alg[dom]/(dom_ms*1e-3)/1e9
+    # bytes one particle-step has to move: 120 (push 80 + deposit 40)
+    # when the two are separate kernels, 80 when the deposit is fused into the push
+    step_bytes = 80.0 if fused else 120.0
     roofline = {"kernel": tkey.get(dom, dom), "bound": "hbm",
                 "achieved": round(dom_gbs, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(dom_gbs/peak, 4),
                 "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg[dom],
+                "alg_bytes_per_particle": 80.0 if dom in ("push", "push_deposit") else
+                (40.0 if dom == "deposit" else None),
                 "ms_per_launch": dom_ms, "timing": how,
                 "frac_best_isolated": kern[dom]["frac"],
-                # whole step against its 120 algorithmic bytes per particle-step
-                # (SURVEY.md §8d: ordering, migration and halo traffic are overhead)
-                "step_frac": round(120.0*npart/(ms/a.steps*1e-3)/1e9/peak, 4)}
-    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+                # whole step against the bytes it has to move per particle-step
+                # (ordering, migration and halo traffic are overhead)
+                "step_bytes_per_particle": step_bytes,
+                "step_frac": round(step_bytes*npart/(ms/a.steps*1e-3)/1e9/peak, 4),
+                "step_frac_unfused_accounting":
+                    round(120.0*npart/(ms/a.steps*1e-3)/1e9/peak, 4)}
+    # the other target kernels of the north star, each on its own bytes
+    others = {}
+    for name in ("push_unfused", "deposit_unfused", "deposit", "push"):
+        src_d = kern if name in kern else standalone
+        if name in src_d and name != dom and "frac" in src_d[name]:
+            others[name] = {k: src_d[name][k] for k in
+                            ("ms", "achieved_gbs", "frac", "live_ms", "live_frac")
+                            if k in src_d[name]}
+    roofline["others"] = others
+    # DRAM traffic: bytes per particle of one `ncu --set full` capture of this kernel at
+    # full size (profiles/traffic_r02.json names the capture), scaled by the particles
+    # this launch processed
+    tr = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(tkey.get(dom, dom))
+            rec = json.load(open(tr)).get(dom)
+            if rec:
+                roofline["traffic"] = rec["dram_bytes_per_particle"]*npart
+                roofline["traffic_source"] = (
+                    "ncu dram__bytes_read.sum + dram__bytes_write.sum of %s, %.1f B per "
+                    "particle, scaled by the %d particles of this launch" % (
+                        rec["capture"], rec["dram_bytes_per_particle"], npart))
         except Exception:
             pass
 
@@ -480,15 +654,19 @@ def b200_arm(a):
                "what": "E,B copied H2D from pinned host memory and sources copied D2H "
                        "inside the timed step; particles stay resident in HBM"}
 
-    # ---- size-independent sanity checks at the full workload size
-    step()
+    # ---- parity at the full workload size (oracle = checker), then conservation
+    checks = {}
+    if not a.no_parity:
+        checks.update(parity_checks(sk, ions, E, B, src, dt, comm, a))
+    else:
+        step()
     n_now = comm.allreduce(int(ions.N), op=sk.comm.SUM) if size > 1 else int(ions.N)
     rho_sum = float(src.t[m.lby:m.uby, m.lbx:m.ubx, 0].sum().item())
     if size > 1:
         rho_sum = comm.allreduce(rho_sum, op=sk.comm.SUM)
     expect = n_total*ions.charge/a.ppc
-    checks = {"particles_conserved": n_now == n_total,
-              "charge_rel_err": abs(rho_sum - expect)/expect}
+    checks.update({"particles_conserved": n_now == n_total,
+                   "charge_rel_err": abs(rho_sum - expect)/expect})
 
     cpu = None
     if rank == 0 and size == 1 and not a.no_cpu_baseline:

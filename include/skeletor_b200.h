@@ -264,13 +264,15 @@ int skb_canonical_cells(skb_particles_t in, skb_particles_t out, const int *cell
  *   change cell go to `movers` (AoS rows; counts[0]), particles that leave the slab to
  *   sbufl / sbufr as skb_move_pack would (counts[1], counts[2]); counts[4] = movers
  *   re-inserted in place (statistics); counts[3] = flags
- *   (1: mover list full, some particles were parked in their old cell -> rebuild;
- *    2: exchange buffer overflow).
+ *   (1: mover list full, some particles were parked in their old cell -> rebuild
+ *       (generic kernel only);  2: exchange buffer overflow;  8: mover lists full,
+ *       particles were lost (cell-stream kernel: size the lists for the step)).
  *   The nleft particles of `leftover` (below) are pushed first, with the generic
  *   kernel, and join the head of the mover list (nleft <= mover_cap).
  *   Movers whose new cell is handled by the same thread block never reach `movers`:
  *   the block parks them in one of npool scratch blocks ([npool][scratch_rows][5]
- *   doubles, pool_owner [npool] zero-initialised; npool >= 592 or 0 to disable) and
+ *   doubles, pool_owner [npool] zero-initialised; npool >= the number of thread blocks
+ *   that can be resident (checked at launch), or 0 to disable) and
  *   inserts them itself; full cells overflow into `leftover` (leftover_counts[0] rows,
  *   [1] overflow flag; both reset by this call after the old leftovers are consumed).
  * skb_gap_insert:  drop AoS rows (movers, arrivals) into the free slots of their cells;
@@ -307,6 +309,27 @@ int skb_push_and_deposit_gapped(skb_particles_t p, const double *E, const double
                                 int nleft, int *leftover_counts, double *scratch,
                                 int scratch_rows, int npool, int *pool_owner,
                                 void *stream);
+/* push / push_modified (particle_push.pyx:4,40,81,117) + boundary epilogue as
+ * skb_push_gapped, fused with the full-step deposit that follows the push in the time
+ * loop (Sources.deposit, sources.py:27-50 -> deposit_cic/tsc, deposit.pyx:6,21): `current`
+ * (zeroed by the caller) receives the RAW stencil sums (dep_S: rate of shear of the
+ * deposit, deposit.pxd:24) of every particle that is in the slab after the push; the
+ * arrivals from the neighbour ranks are added with skb_deposit_rows.  counts[3] bit 8:
+ * mover lists full, particles were lost (fatal); bit 16: some rows bypassed the fused
+ * deposit (scratch block full) - discard `current` and call skb_deposit. */
+int skb_push_deposit_gapped(skb_particles_t p, const double *E, const double *B,
+                            const skb_grid_t *grid, int order, double qtmh, double dt,
+                            int modified, double Omega, double S, int epi_flags,
+                            double epi_S, double epi_t, double *current, double dep_S,
+                            int tlx, int tly, const int *gap_start, int *gap_count,
+                            double *movers, int mover_cap, double *sbufl, double *sbufr,
+                            int nbmax, int *counts, int rank, int nvp, double *leftover,
+                            int leftover_cap, int nleft, int *leftover_counts,
+                            double *scratch, int scratch_rows, int npool, int *pool_owner,
+                            void *stream);
+/* deposit_cic/tsc (deposit.pyx:6,21) of n AoS rows {x, y, vx, vy, vz} into `current` */
+int skb_deposit_rows(const double *rows, int n, double *current, const skb_grid_t *grid,
+                     int order, double S, void *stream);
 int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
                    int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
                    double *leftover, int leftover_cap, int *counts, void *stream);

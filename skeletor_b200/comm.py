@@ -144,6 +144,16 @@ class TorchComm:
         below = (self.rank - 1) % self.size
         from_below = torch.empty_like(up) if recv_below is None else recv_below
         from_above = torch.empty_like(down) if recv_above is None else recv_above
+        if self.backend != "nccl" and up.is_cuda:
+            # gloo has no device-side send/recv: the MESSAGES are staged through host
+            # memory (several ranks sharing one GPU in the 1-GPU parity tests; every
+            # kernel still runs on the device)
+            fb, fa = self.ring_exchange(up.cpu(), down.cpu(),
+                                        torch.empty(from_below.shape, dtype=up.dtype),
+                                        torch.empty(from_above.shape, dtype=down.dtype))
+            from_below.copy_(fb)
+            from_above.copy_(fa)
+            return from_below, from_above
         if self.size == 2:
             # both neighbours are the same peer: order the two messages explicitly
             ops = [dist.P2POp(dist.isend, up, above, self.group, tag=0),
@@ -200,8 +210,12 @@ def init_world():
         _world = TorchComm()
     elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
-        if backend == "nccl":
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        # SKELETOR_B200_BACKEND=gloo: several ranks on ONE GPU (NCCL refuses that);
+        # used by the 1-GPU run of tests/test_gpu_multirank.py
+        backend = os.environ.get("SKELETOR_B200_BACKEND", backend)
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")) %
+                                  torch.cuda.device_count())
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend=backend)
         _world = TorchComm()

@@ -1,0 +1,678 @@
+// cellstream.cu — the push on the gapped particle layout as a TMA-fed cell stream (sm_100a).
+//
+// Same work as push_gapped_kernel (gapped.cu): gather E,B -> Boris kick -> drift -> shear
+// boost / x wrap -> route (stay in the cell, move to another cell, leave the slab), i.e.
+// reference particles.py:159-188 / 233-257 in one pass, and optionally the full-step
+// deposit that normally follows it (sources.py:27-50, deposit.pyx:6-34) fused in.  It is
+// organised around what ncu showed about that kernel (514 warp instructions per 32
+// particles, two thirds of the issue slots busy, 145 of them fp64 arithmetic):
+//
+//  * one warp streams the particles of one ROW of 16 cells of a 16 x 16 tile; a CTA of 8
+//    warps owns half a tile and stages its own (8+5) x (16+5) window of E and B;
+//  * particles arrive through a per-warp ring of 64-particle stages filled by TMA 1-D bulk
+//    copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx): lanes 0..4
+//    issue ONE copy each (x, y, vx, vy, vz), nobody computes per-lane load addresses;
+//  * all particles of a cell share the E stencil (the sort key IS the E-gather / deposit
+//    base cell), so for CIC the 2 x 2 x 3 E values live in registers for the whole cell;
+//    B is read per lane from the shared window (its base cell differs by the half-cell
+//    offset, particle_push.pyx:15-19);
+//  * stayers are written back compacted to the front of the cell's slot range;
+//  * every particle that changes cell is staged as an AoS row in a per-warp shared-memory
+//    buffer and flushed 32 rows (1280 B) at a time with ONE TMA bulk store
+//    (cp.async.bulk.global.shared::cta) into the CTA's scratch block; after the stream the
+//    CTA classifies those rows with all lanes busy: rows for its own cells go into their
+//    free slots (warp-aggregated claims), the rest onto the global mover list;
+//  * (PD = 3) stayers accumulate their full-step stencil sums in registers, one warp
+//    reduce-scatter + emit per cell into a shared window of the sources grid; the rows
+//    the CTA re-inserted are accumulated the same way in a second sweep over the cells'
+//    new tails, rows that leave the CTA are deposited one by one.
+//
+// Per-particle arithmetic keeps the reference's operation order (-fmad=false), so the
+// results are bit-identical to push_gapped_kernel / the oracle.
+#include <cstdlib>
+#include "gapped.cuh"
+
+#define CS_THREADS 256
+#define CS_WARPS 8
+#define CS_CPW 16            // cells per warp: one row of the 16 x 16 tile
+#define CS_CELLS 128         // cells per CTA: half a tile
+#define CS_STAGE 64          // particles per ring stage
+#ifndef CS_NST
+#define CS_NST 3             // ring stages per warp
+#endif
+#ifndef CS_MINB
+#define CS_MINB 2            // resident CTAs per SM aimed at
+#endif
+#define CS_MROWS 64          // mover rows buffered per warp: two halves of 32
+#define CS_WS 21             // window stride in cells: 16 + SKB_HALO_LO + SKB_HALO_HI
+#define CS_WR 13             // window rows of a half tile: 8 + SKB_HALO_LO + SKB_HALO_HI
+#define CS_WIN3 832          // doubles reserved per Float3 window (13*21*3 = 819, 128 B multiple)
+#define CS_WIN4 1104         // doubles reserved for the Float4 window (13*21*4 = 1092)
+#define CS_STAGE_D (5 * CS_STAGE)   // doubles per ring stage
+
+// ---- PTX wrappers: mbarrier + TMA bulk copies ----------------------------------------
+__device__ __forceinline__ unsigned cs_smem(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cs_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cs_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool cs_mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// global -> shared, completion signalled on the mbarrier (bytes: multiple of 16; both
+// addresses 16-byte aligned)
+__device__ __forceinline__ void cs_bulk_load(unsigned dst, const void *src, unsigned bytes,
+                                             unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void cs_bulk_store(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cs_bulk_wait_read() {      // sources may be overwritten
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void cs_bulk_wait_all() {       // writes are complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void cs_fence_async_smem() {    // generic-proxy STS -> TMA reads
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- phase B: the rows the CTA parked in its scratch block ---------------------------
+// Rows i0 + t*256 (t < GAP_INS_ITEMS, < n) of `rows` (AoS, global): rows whose cell is one
+// of this CTA's cells [c0, c0 + CS_CELLS) are dropped into the free slots of that cell
+// (one slot claim per warp and destination cell, as gap_insert_rows); the others are
+// appended to the global mover list for skb_gap_insert.  PD: rows that do not end up in
+// one of the CTA's cells are deposited here, one by one (shared window or HBM atomics);
+// the re-inserted ones are deposited from the cells' tails afterwards.  Warp-collective.
+template <int ORDER, int PD>
+__device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, int n, int i0,
+                                              skb_particles_t P, const GapPush &q,
+                                              const GapDeposit &dq, const DevGrid &g,
+                                              const Window &w, double *sS, int c0) {
+  constexpr int NS = ORDER + 1;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  double r0[GAP_INS_ITEMS], r1[GAP_INS_ITEMS], r2[GAP_INS_ITEMS], r3[GAP_INS_ITEMS],
+      r4[GAP_INS_ITEMS];
+  bool valid[GAP_INS_ITEMS];
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    const int i = i0 + t * CS_THREADS;
+    valid[t] = i < n;
+    r0[t] = r1[t] = r2[t] = r3[t] = r4[t] = 0.0;
+    if (valid[t]) {
+      const double *r = rows + (size_t)i * 5;
+      r0[t] = __ldcg(r); r1[t] = __ldcg(r + 1); r2[t] = __ldcg(r + 2);
+      r3[t] = __ldcg(r + 3); r4[t] = __ldcg(r + 4);
+    }
+  }
+  int key[GAP_INS_ITEMS], s[GAP_INS_ITEMS], cap[GAP_INS_ITEMS], base[GAP_INS_ITEMS],
+      rank[GAP_INS_ITEMS], leader[GAP_INS_ITEMS];
+  bool local[GAP_INS_ITEMS];
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    valid[t] = valid[t] && __double_as_longlong(r0[t]) != GAP_PAD_BITS;
+    key[t] = valid[t] ? cell_key(r0[t], r1[t], q.key) : -1;
+    local[t] = valid[t] && (unsigned)(key[t] - c0) < (unsigned)CS_CELLS;
+    const unsigned peers = __match_any_sync(SKB_FULL, local[t] ? key[t] : -1 - lane);
+    const int cnt = __popc(peers);
+    leader[t] = __ffs(peers) - 1; rank[t] = __popc(peers & lt);
+    s[t] = cap[t] = base[t] = 0;
+    if (local[t] && lane == leader[t]) {
+      base[t] = atomicAdd(q.gap_count + key[t], cnt);
+      s[t] = q.gap_start[key[t]]; cap[t] = q.gap_start[key[t] + 1] - s[t];
+      const int over = min(max(base[t] + cnt - cap[t], 0), cnt);
+      if (over) atomicSub(q.gap_count + key[t], over);  // cell full: those go to the leftovers
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < GAP_INS_ITEMS; t++) {
+    const int ss = __shfl_sync(SKB_FULL, s[t], leader[t]);
+    const int cc = __shfl_sync(SKB_FULL, cap[t], leader[t]);
+    const int slot = __shfl_sync(SKB_FULL, base[t], leader[t]) + rank[t];
+    bool placed = false;
+    if (local[t]) {
+      if (slot < cc) {
+        const long long d = (long long)ss + slot;
+        P.x[d] = r0[t]; P.y[d] = r1[t]; P.vx[d] = r2[t]; P.vy[d] = r3[t]; P.vz[d] = r4[t];
+        placed = true;
+      } else {
+        const int l = atomicAdd(q.lcounts + 0, 1);
+        if (l < q.leftover_cap) {
+          const size_t lc = (size_t)q.leftover_cap;
+          q.leftover[l] = r0[t]; q.leftover[lc + l] = r1[t]; q.leftover[2 * lc + l] = r2[t];
+          q.leftover[3 * lc + l] = r3[t]; q.leftover[4 * lc + l] = r4[t];
+        } else {
+          q.lcounts[1] = 1;                         // even the leftover list is full
+        }
+      }
+    }
+    // rows for other CTAs' cells: global mover list, one reservation per warp
+    const bool fwd = valid[t] && !local[t];
+    const unsigned fm = __ballot_sync(SKB_FULL, fwd);
+    if (fm) {
+      int fb = 0;
+      if (lane == __ffs(fm) - 1) fb = atomicAdd(q.counts + 0, __popc(fm));
+      fb = __shfl_sync(SKB_FULL, fb, __ffs(fm) - 1);
+      if (fwd) {
+        const int ms = fb + __popc(fm & lt);
+        if (ms < q.mover_cap) {
+          double *o = q.movers + (size_t)ms * 5;
+          o[0] = r0[t]; o[1] = r1[t]; o[2] = r2[t]; o[3] = r3[t]; o[4] = r4[t];
+        } else {
+          atomicOr(q.counts + 3, 8);                // list full: the particle is lost
+        }
+      }
+    }
+    if constexpr (PD != 0) {
+      if (valid[t] && !placed) {
+        double xs = r0[t] + dq.dp.offx, ys = r1[t] + dq.dp.offy;
+        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+        int ix, iy;
+        double wx[NS], wy[NS];
+        particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+        const double vxr = r2[t] + dq.dp.S * (r1[t] * g.dy + g.y0);
+        stray_particle_emit<NS>(wx, wy, ix, iy, vxr, r3[t], r4[t], sS, w, CS_WS, dq.cur, g);
+      }
+    }
+  }
+}
+
+// Reserve room for 32 mover rows (one half of a warp's buffer): in the CTA's scratch block
+// if it has room, else on the global mover list (rows there bypass phase B: with PD the
+// caller redoes the deposit, flag 16).  Returns NULL when both are full: the warp then
+// parks its movers in their old cells (flag 1: the layout is rebuilt).  Every reservation
+// that succeeds is later written in full (rows or padding).  Warp-collective.
+template <int PD>
+__device__ __forceinline__ double *cs_reserve(int *s_nrows, double *scr, int scr_rows,
+                                              const GapPush &q) {
+  const int lane = threadIdx.x & 31;
+  int slot = 0;
+  if (lane == 0) slot = atomicAdd(s_nrows, 32);
+  slot = __shfl_sync(SKB_FULL, slot, 0);
+  if (slot + 32 <= scr_rows) return scr + (size_t)slot * 5;
+  // 33 rows: the list head may be odd (leftover rows), a TMA store needs 16-byte rows
+  int gs = 0;
+  if (lane == 0) gs = atomicAdd(q.counts + 0, 33);
+  gs = __shfl_sync(SKB_FULL, gs, 0);
+  if (gs + 33 <= q.mover_cap) {
+    const int ge = (gs + 1) & ~1;
+    if (lane == 0) {
+      q.movers[(size_t)(gs == ge ? gs + 32 : gs) * 5] = __longlong_as_double(GAP_PAD_BITS);
+      if (PD != 0) atomicOr(q.counts + 3, 16);
+    }
+    return q.movers + (size_t)ge * 5;
+  }
+  // no room: whatever part of the reservation lies inside the list becomes padding
+  for (int r = gs + lane; r < min(gs + 33, q.mover_cap); r += 32)
+    q.movers[(size_t)r * 5] = __longlong_as_double(GAP_PAD_BITS);
+  if (lane == 0) atomicOr(q.counts + 3, 1);
+  return nullptr;
+}
+
+// ---- the kernel --------------------------------------------------------------------------
+// PD = 0: push;  PD = 3: push + full-step deposit into dq.cur (raw sums, not normalised)
+template <int ORDER, bool MODIFIED, int PD>
+__global__ void __launch_bounds__(CS_THREADS, (ORDER == 2 && PD != 0) ? 1 : CS_MINB)
+cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
+                   const double *__restrict__ B, DevGrid g, GapPush q, GapDeposit dq) {
+  constexpr int NS = ORDER + 1;
+  constexpr int LO = (ORDER == 2) ? 1 : 0;
+  extern __shared__ __align__(128) double smem[];
+  double *sE = smem;
+  double *sB = sE + CS_WIN3;
+  double *sS = sB + CS_WIN3;                                  // (PD) window of the sources
+  double *rings = sS + (PD ? CS_WIN4 : 0);                    // [warps][CS_NST][5][CS_STAGE]
+  double *mbufs = rings + CS_WARPS * CS_NST * CS_STAGE_D;     // [warps][CS_MROWS][5]
+  unsigned long long *bars = (unsigned long long *)(mbufs + CS_WARPS * CS_MROWS * 5);
+  __shared__ int s_blk, s_nrows;
+  __shared__ int s_nstay[CS_CELLS];
+
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int c0 = (tile << 8) + (half << 7);
+  const int wc0 = c0 + wv * CS_CPW;
+  // my cells: lane j < 16 holds the slot range and the count of cell wc0 + j
+  const int my_cnt = lane < CS_CPW ? q.gap_count[wc0 + lane] : 0;
+  const int my_start = lane < CS_CPW ? q.gap_start[wc0 + lane] : 0;
+  if (!__syncthreads_or(my_cnt)) return;                     // nothing lives here
+  const int bx = (tile % q.key.ntx) << 4;
+  const int by = ((tile / q.key.ntx) << 4) + (half << 3);
+  Window w;
+  w.x0 = max(bx - SKB_HALO_LO, 0); w.y0 = max(by - SKB_HALO_LO, 0);
+  w.x1 = min(bx + 16 + SKB_HALO_HI, g.mx); w.y1 = min(by + 8 + SKB_HALO_HI, g.myp);
+  if (threadIdx.x == 0) {
+    int b = -1;
+    if (q.npool > 0) {
+      b = blockIdx.x % q.npool;
+      while (atomicCAS(q.pool_owner + b, 0, 1) != 0) b = (b + 1 == q.npool) ? 0 : b + 1;
+    }
+    s_blk = b; s_nrows = 0;
+  }
+  if (threadIdx.x < CS_CELLS) s_nstay[threadIdx.x] = 0;
+  const unsigned bar0 = cs_smem(bars + wv * CS_NST);
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < CS_NST; st++) cs_mbar_init(bar0 + 8 * st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (PD != 0) zero_window(sS, CS_WIN4);
+  stage_window(sE, E, w, CS_WS, g);
+  stage_window(sB, B, w, CS_WS, g);
+  __syncthreads();
+  double *const scr = s_blk >= 0 ? q.scratch + (size_t)s_blk * q.scratch_rows * 5 : nullptr;
+  const int scr_rows = s_blk >= 0 ? q.scratch_rows : 0;
+  const double nxd = (double)g.nx, nyd = (double)g.ny;
+  const int ciy = by + wv;
+  // lanes 0..4 feed the ring: lane k copies array k
+  const double *const my_arr = lane == 0 ? P.x : lane == 1 ? P.y : lane == 2 ? P.vx
+                               : lane == 3 ? P.vy : P.vz;
+  double *const ring = rings + (size_t)wv * (CS_NST * CS_STAGE_D);
+  const unsigned ring_s = cs_smem(ring);
+  double *const mbuf = mbufs + (size_t)wv * (CS_MROWS * 5);
+  int mcount = 0;                                  // mover rows staged so far by this warp
+  double *cur_dst = nullptr;                       // where the half being filled will go
+  bool parking = false;                            // mover lists full: movers stay put
+
+#define CS_CNT(j) __shfl_sync(SKB_FULL, my_cnt, (j))
+#define CS_ADVANCE(j, base)                                    \
+  do {                                                         \
+    base += CS_STAGE;                                          \
+    if (base >= CS_CNT(j)) {                                   \
+      base = 0; j++;                                           \
+      while (j < CS_CPW && CS_CNT(j) == 0) j++;                \
+    }                                                          \
+  } while (0)
+  // one stage = up to 64 particles of ONE cell: 5 bulk copies of `bytes` each
+#define CS_FETCH(stage, j, base)                                                        \
+  do {                                                                                  \
+    const int fs_ = __shfl_sync(SKB_FULL, my_start, (j));                               \
+    const int np_ = (min(CS_STAGE, CS_CNT(j) - (base)) + 1) & ~1;                       \
+    const unsigned bar_ = bar0 + 8 * (stage);                                           \
+    if (lane == 0) cs_mbar_expect_tx(bar_, 5u * 8u * (unsigned)np_);                    \
+    if (lane < 5)                                                                       \
+      cs_bulk_load(ring_s + (unsigned)(((stage) * 5 + lane) * CS_STAGE) * 8u,           \
+                   my_arr + ((size_t)fs_ + (base)), 8u * (unsigned)np_, bar_);          \
+  } while (0)
+
+  int fj = 0, fbase = 0;
+  while (fj < CS_CPW && CS_CNT(fj) == 0) fj++;
+  int cj = fj, cbase = 0;
+#pragma unroll
+  for (int st = 0; st < CS_NST; st++)
+    if (fj < CS_CPW) { CS_FETCH(st, fj, fbase); CS_ADVANCE(fj, fbase); }
+  int stage = 0, wcur = 0;                         // wcur: stayers written so far
+  unsigned phases = 0;                             // parity bit of every ring stage
+  Acc<NS> acc;                                     // (PD) stencil sums of the current cell
+  double eC[4][3];                                 // (CIC) E stencil of the current cell
+  bool cell_fast = false;
+  int cix = 0, s = 0, n = 0;
+  while (cj < CS_CPW) {
+    if (cbase == 0) {                              // first stage of a cell
+      cix = bx + cj;
+      s = __shfl_sync(SKB_FULL, my_start, cj);
+      n = CS_CNT(cj);
+      // every stencil a particle filed under this cell can touch lies inside the window
+      cell_fast = cix - LO >= w.x0 && cix + 2 < w.x1 && ciy - LO >= w.y0 && ciy + 2 < w.y1;
+      if (ORDER == 1 && cell_fast) {
+        const double *eb = sE + ((ciy - w.y0) * CS_WS + (cix - w.x0)) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          eC[0][k] = eb[k]; eC[1][k] = eb[3 + k];
+          eC[2][k] = eb[CS_WS * 3 + k]; eC[3][k] = eb[CS_WS * 3 + 3 + k];
+        }
+      }
+      if constexpr (PD != 0) {
+#pragma unroll
+        for (int i = 0; i < NS * NS * 4; i++) acc.v[i] = 0.0;
+        acc.ix = cix; acc.iy = ciy;
+      }
+    }
+    while (!cs_mbar_try_wait(bar0 + 8 * stage, (phases >> stage) & 1u)) {}
+    phases ^= 1u << stage;
+    const double *pb = ring + stage * CS_STAGE_D;
+    const int nrem = n - cbase;
+#pragma unroll 1
+    for (int u = 0; u < CS_STAGE / 32; u++) {
+      if (u * 32 >= nrem) break;
+      const bool act = u * 32 + lane < nrem;
+      bool stay = false, mover = false, parked = false;
+      int nix = 0, niy = 0;
+      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
+      double wx[NS], wy[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) wx[i] = wy[i] = 0.0;
+      if (act) {
+        const double *pp = pb + u * 32 + lane;
+        x = pp[0]; y = pp[CS_STAGE]; vx = pp[2 * CS_STAGE]; vy = pp[3 * CS_STAGE];
+        vz = pp[4 * CS_STAGE];
+      }
+      // field gather: shared stencil of the cell (E) / per-lane window reads (B); a lane
+      // whose indices are not the ones its cell promises sends the warp down the generic
+      // path for this block
+      double xe = x + q.k.offEx, ye = y + q.k.offEy, xb = x + q.k.offBx, yb = y + q.k.offBy;
+      if (ORDER == 2) { xe = xe + 0.5; ye = ye + 0.5; xb = xb + 0.5; yb = yb + 0.5; }
+      const int ixe = (int)xe, iye = (int)ye, ixb = (int)xb, iyb = (int)yb;
+      const bool ok = !act || (ixe == cix && iye == ciy && (unsigned)(ixb - cix) <= 1u &&
+                               (unsigned)(iyb - ciy) <= 1u);
+      if (cell_fast && __all_sync(SKB_FULL, ok)) {
+        if (act) {
+          double e[3], b[3];
+          if constexpr (ORDER == 1) {
+            const double dx = xe - (double)ixe, tx = 1.0 - dx;
+            const double dy = ye - (double)iye, ty = 1.0 - dy;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              e[k] = dy * (dx * eC[3][k] + tx * eC[2][k]) + ty * (dx * eC[1][k] + tx * eC[0][k]);
+            const double *bp = sB + ((iyb - w.y0) * CS_WS + (ixb - w.x0)) * 3;
+            const double dxb = xb - (double)ixb, txb = 1.0 - dxb;
+            const double dyb = yb - (double)iyb, tyb = 1.0 - dyb;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              b[k] = dyb * (dxb * bp[(CS_WS + 1) * 3 + k] + txb * bp[CS_WS * 3 + k]) +
+                     tyb * (dxb * bp[3 + k] + txb * bp[k]);
+          } else {
+            // tsc_weights, particle_push.pxd:37-57 (xe, xb already carry the + 0.5)
+            double wmx, w0x, wpx, wmy, w0y, wpy;
+            {
+              const double d = xe - (double)ixe - 0.5; w0x = 0.75 - d * d;
+              const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
+            }
+            {
+              const double d = ye - (double)iye - 0.5; w0y = 0.75 - d * d;
+              const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
+            }
+            const double *ep = sE + ((ciy - 1 - w.y0) * CS_WS + (cix - 1 - w.x0)) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              e[k] = wmy * (wmx * ep[k] + w0x * ep[3 + k] + wpx * ep[6 + k]) +
+                     w0y * (wmx * ep[CS_WS * 3 + k] + w0x * ep[CS_WS * 3 + 3 + k] +
+                            wpx * ep[CS_WS * 3 + 6 + k]) +
+                     wpy * (wmx * ep[2 * CS_WS * 3 + k] + w0x * ep[2 * CS_WS * 3 + 3 + k] +
+                            wpx * ep[2 * CS_WS * 3 + 6 + k]);
+            {
+              const double d = xb - (double)ixb - 0.5; w0x = 0.75 - d * d;
+              const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
+            }
+            {
+              const double d = yb - (double)iyb - 0.5; w0y = 0.75 - d * d;
+              const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
+            }
+            const double *bp = sB + ((iyb - 1 - w.y0) * CS_WS + (ixb - 1 - w.x0)) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+              b[k] = wmy * (wmx * bp[k] + w0x * bp[3 + k] + wpx * bp[6 + k]) +
+                     w0y * (wmx * bp[CS_WS * 3 + k] + w0x * bp[CS_WS * 3 + 3 + k] +
+                            wpx * bp[CS_WS * 3 + 6 + k]) +
+                     wpy * (wmx * bp[2 * CS_WS * 3 + k] + w0x * bp[2 * CS_WS * 3 + 3 + k] +
+                            wpx * bp[2 * CS_WS * 3 + 6 + k]);
+          }
+          rescale_and_kick<MODIFIED>(e, b, g, q.k, y, vx, vy, vz);
+        }
+      } else if (act) {
+        fields_and_kick<ORDER, MODIFIED>(sE, sB, w, CS_WS, E, B, g, q.k, x, y, vx, vy, vz);
+      }
+      bool leaver = false;
+      if (act) {
+        x = x + vx * q.dtdsx;                      // drift_particle, particle_push.pxd:88-91
+        y = y + vy * q.dtdsy;
+        if (q.flags & SKB_EPI_SHEAR) {             // particle_boundary.pyx:41-49
+          if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
+          if (y >= nyd) { x = x + q.x_boost; vx = vx + q.vx_boost; }
+        }
+        if ((q.flags & SKB_EPI_PERIODIC_X) && !(x >= 0.0 && x < nxd)) x = wrap_x(x, nxd);
+        leaver = y < g.e0 || y >= g.e1;
+        // new stencil-base cell (== cell_key without the clamp: a particle outside the
+        // array is a mover and gets clamped by the insertion) and, for PD, the weights
+        double xs = x + q.key.offx, ys = y + q.key.offy;
+        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+        particle_terms<ORDER>(xs, ys, nix, niy, wx, wy);
+        stay = !leaver && nix == cix && niy == ciy;
+        mover = !leaver && !stay;
+      }
+      if (__any_sync(SKB_FULL, leaver)) {
+        if (leaver) {                              // leaves the slab: cppmove2's pack
+          double *buf; int slot; double yy = y;
+          if (yy < g.e0) {
+            if (q.rank == 0) yy += nyd;
+            slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
+          } else {
+            if (q.rank == q.nvp - 1) yy -= nyd;
+            slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
+          }
+          if (slot < q.nbmax) {
+            double *r = buf + (size_t)slot * 5;
+            r[0] = x; r[1] = yy; r[2] = vx; r[3] = vy; r[4] = vz;
+          } else {
+            atomicOr(q.counts + 3, 2);
+          }
+        }
+      }
+      // movers: AoS rows in the warp's shared buffer; a half (32 rows, 1280 B) goes out
+      // with one TMA bulk store to a destination reserved BEFORE its first row is staged
+      const unsigned mm = __ballot_sync(SKB_FULL, mover);
+      if (mm) {
+        if (!parking && cur_dst == nullptr) {
+          cur_dst = cs_reserve<PD>(&s_nrows, scr, scr_rows & ~31, q);
+          parking = cur_dst == nullptr;
+        }
+        if (parking) {
+          parked = mover; stay = stay || mover; mover = false;
+        } else {
+          const int after = mcount + __popc(mm);
+          const int boundary = (mcount | 31) + 1;
+          const bool cross = after >= boundary;
+          double *nxt = nullptr;
+          if (cross) {          // the half about to be (re)entered must have been read out
+            if (lane == 0) cs_bulk_wait_read();
+            __syncwarp();
+            if (after > boundary) {
+              nxt = cs_reserve<PD>(&s_nrows, scr, scr_rows & ~31, q);
+              parking = nxt == nullptr;
+            }
+          }
+          if (mover) {
+            const int pos = mcount + __popc(mm & lt);
+            if (parking && pos >= boundary) {
+              parked = true; stay = true; mover = false;
+            } else {
+              double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
+              r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+            }
+          }
+          if (cross) {
+            const int h = (mcount >> 5) & 1;       // the half that is complete now
+            cs_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) cs_bulk_store(cur_dst, cs_smem(mbuf + h * 160), 1280u);
+            cur_dst = nxt;
+          }
+          mcount = (cross && parking) ? boundary : after;
+        }
+      }
+      // stayers: compacted to the front of the cell's range (always behind the reads:
+      // wcur <= cbase + u*32, and everything up to cbase + 64 is already in the ring)
+      const unsigned sm = __ballot_sync(SKB_FULL, stay);
+      if (stay) {
+        const long long d = (long long)s + wcur + __popc(sm & lt);
+        P.x[d] = x; P.y[d] = y; P.vx[d] = vx; P.vy[d] = vy; P.vz[d] = vz;
+        if constexpr (PD != 0) {
+          const double vxr = vx + dq.dp.S * (y * g.dy + g.y0);     // deposit.pxd:24
+          if (!parked) accumulate<ORDER>(acc, wx, wy, vxr, vy, vz);
+          else stray_particle_emit<NS>(wx, wy, nix, niy, vxr, vy, vz, sS, w, CS_WS, dq.cur, g);
+        }
+      }
+      wcur += __popc(sm);
+    }
+    __syncwarp();                                  // stage fully read: refill it
+    int nj = cj, nbase = cbase;
+    CS_ADVANCE(nj, nbase);
+    if (nj != cj) {                                // the cell is finished
+      if (lane == 0) { q.gap_count[wc0 + cj] = wcur; s_nstay[wv * CS_CPW + cj] = wcur; }
+      wcur = 0;
+      if constexpr (PD != 0) {
+        // one warp reduction and one emit per cell (see deposit_cells_kernel)
+        const bool in_window = cell_fast;
+        if constexpr (NS == 2) {
+          warp_reduce_scatter<16>(acc.v, lane);
+          if (lane < 16)
+            emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sS, w,
+                         CS_WS, dq.cur, g);
+        } else {
+          warp_reduce_scatter<32>(acc.v, lane);
+          warp_reduce_scatter<4>(acc.v + 32, lane);
+          emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sS, w,
+                       CS_WS, dq.cur, g);
+          if (lane < 4)
+            emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sS,
+                         w, CS_WS, dq.cur, g);
+        }
+      }
+    }
+    cj = nj; cbase = nbase;
+    if (fj < CS_CPW) { CS_FETCH(stage, fj, fbase); CS_ADVANCE(fj, fbase); }
+    stage = (stage + 1 == CS_NST) ? 0 : stage + 1;
+  }
+#undef CS_CNT
+#undef CS_ADVANCE
+#undef CS_FETCH
+  // the rows still in the warp's buffer: the unused part of the half becomes padding
+  {
+    const int rem = mcount & 31;
+    if (rem && cur_dst != nullptr) {
+      const int h = (mcount >> 5) & 1;
+      if (lane >= rem) mbuf[(h * 32 + lane) * 5] = __longlong_as_double(GAP_PAD_BITS);
+      cs_fence_async_smem();
+      __syncwarp();
+      if (lane == 0) cs_bulk_store(cur_dst, cs_smem(mbuf + h * 160), 1280u);
+    }
+    if (lane == 0) cs_bulk_wait_all();             // my scratch rows are in memory
+  }
+  // phase B: all cells of this CTA are compacted; place the parked rows
+  __syncthreads();
+  const int nrows = min(s_nrows, scr_rows & ~31);  // (reservations are whole halves)
+  if (nrows > 0) {
+    if (threadIdx.x == 0) atomicAdd(q.counts + 4, nrows);            // statistics
+    for (int r0 = 0; r0 < nrows; r0 += CS_THREADS * GAP_INS_ITEMS)
+      cs_place_rows<ORDER, PD>(scr, nrows, r0 + (int)threadIdx.x, P, q, dq, g, w, sS, c0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_blk >= 0) atomicExch(q.pool_owner + s_blk, 0);
+  if constexpr (PD != 0) {
+    // the rows re-inserted above sit behind the stayers of their cells: accumulate them
+    // like the stayers (same cell => same stencil), one reduction + emit per cell
+    for (int j = 0; j < CS_CPW; j++) {
+      const int cell = wc0 + j;
+      const int n0 = s_nstay[wv * CS_CPW + j];
+      const int n1 = __ldcg(q.gap_count + cell);
+      if (n1 <= n0) continue;
+      const int st = __shfl_sync(SKB_FULL, my_start, j);
+      const int ax = bx + j;
+#pragma unroll
+      for (int i = 0; i < NS * NS * 4; i++) acc.v[i] = 0.0;
+      acc.ix = ax; acc.iy = ciy;
+      for (int i = n0 + lane; i < n1; i += 32) {
+        const long long d = (long long)st + i;
+        const double x = __ldcg(P.x + d), y = __ldcg(P.y + d), vx = __ldcg(P.vx + d),
+                     vy = __ldcg(P.vy + d), vz = __ldcg(P.vz + d);
+        double xs = x + dq.dp.offx, ys = y + dq.dp.offy;
+        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+        int ix, iy;
+        double wx[NS], wy[NS];
+        particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+        const double vxr = vx + dq.dp.S * (y * g.dy + g.y0);
+        if (ix == acc.ix && iy == acc.iy) accumulate<ORDER>(acc, wx, wy, vxr, vy, vz);
+        else stray_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, sS, w, CS_WS, dq.cur, g);
+      }
+      const bool in_window = ax - LO >= w.x0 && ax + 2 < w.x1 && ciy - LO >= w.y0 &&
+                             ciy + 2 < w.y1;
+      if constexpr (NS == 2) {
+        warp_reduce_scatter<16>(acc.v, lane);
+        if (lane < 16)
+          emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sS, w,
+                       CS_WS, dq.cur, g);
+      } else {
+        warp_reduce_scatter<32>(acc.v, lane);
+        warp_reduce_scatter<4>(acc.v + 32, lane);
+        emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sS, w,
+                     CS_WS, dq.cur, g);
+        if (lane < 4)
+          emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sS,
+                       w, CS_WS, dq.cur, g);
+      }
+    }
+    __syncthreads();
+    flush_window(sS, w, CS_WS, dq.cur, g);
+  }
+}
+
+// ---- launch ---------------------------------------------------------------------------------
+size_t cell_stream_smem(int pd) {
+  return (size_t)(2 * CS_WIN3 + (pd ? CS_WIN4 : 0) + CS_WARPS * CS_NST * CS_STAGE_D +
+                  CS_WARPS * CS_MROWS * 5) * sizeof(double) +
+         CS_WARPS * CS_NST * sizeof(unsigned long long);
+}
+
+// pd: 0 = push, 3 = push + full-step deposit.  Returns cudaErrorNotSupported when the
+// configuration is not the one this kernel is built for (the caller then uses the
+// generic kernel of gapped.cu).
+int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const double *E,
+                       const double *B, const DevGrid &g, const GapPush &q,
+                       const GapDeposit &dq, int ntiles, cudaStream_t st) {
+  if (q.key.tlx != 4 || q.key.tly != 4) return (int)cudaErrorNotSupported;
+  if (pd != 0 && pd != 3) return (int)cudaErrorNotSupported;
+  if (q.scratch_rows & 1) return (int)cudaErrorInvalidValue;     // 16-byte rows for TMA
+  void (*k)(skb_particles_t, const double *, const double *, DevGrid, GapPush, GapDeposit);
+  if (pd == 0) {
+    if (order == 1) k = modified ? cell_stream_kernel<1, true, 0> : cell_stream_kernel<1, false, 0>;
+    else k = modified ? cell_stream_kernel<2, true, 0> : cell_stream_kernel<2, false, 0>;
+  } else {
+    if (order == 1) k = modified ? cell_stream_kernel<1, true, 3> : cell_stream_kernel<1, false, 3>;
+    else k = modified ? cell_stream_kernel<2, true, 3> : cell_stream_kernel<2, false, 3>;
+  }
+  const size_t smem = cell_stream_smem(pd);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  // the scratch-pool claim spins until a block is free: the pool must hold at least as
+  // many blocks as CTAs can be resident
+  if (q.npool > 0) {
+    static int resident[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int slot = (order - 1) * 4 + (modified ? 2 : 0) + (pd ? 1 : 0);
+    if (resident[slot] == 0) {
+      int dev = 0, sms = 0, per = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, CS_THREADS, smem);
+      if (e != cudaSuccess) return (int)e;
+      resident[slot] = max(per, 1) * max(sms, 1);
+    }
+    if (q.npool < resident[slot]) return (int)cudaErrorInvalidValue;
+  }
+  k<<<ntiles * 2, CS_THREADS, smem, st>>>(p, E, B, g, q, dq);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}

@@ -25,11 +25,8 @@
 //
 // New component (no reference counterpart); ordering stays a performance property.
 #include <cstdlib>
-#include "common.cuh"
-#include "gather.cuh"
-#include "deposit.cuh"
+#include "gapped.cuh"
 
-#define GAP_THREADS 256
 #ifndef GAP_MINB
 #define GAP_MINB 3        // resident CTAs/SM aimed at for CIC (80 registers, no spills)
 #endif
@@ -107,11 +104,15 @@ gap_append_rows_kernel(const double *__restrict__ lo, int cap, int n, skb_partic
   out.vz[at + i] = lo[4 * (size_t)cap + i];
 }
 
-// pushed leftover particles (SoA) -> exchange buffers or the head of the mover list
+// pushed leftover particles (SoA) -> exchange buffers or the head of the mover list;
+// cur != NULL (fused full-step deposit): the rows that stay in the slab are deposited
+// here, one by one (the leavers are deposited by the rank that receives them)
+template <int ORDER>
 __global__ void __launch_bounds__(256)
 gap_route_kernel(const double *__restrict__ lo, int cap, int n, double e0, double e1,
                  double ny, int rank, int nvp, double *movers, double *sbufl,
-                 double *sbufr, int nbmax, int *counts) {
+                 double *sbufr, int nbmax, int *counts, double *cur, DepParams dp,
+                 DevGrid g) {
   int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const double x = lo[i], vx = lo[2 * (size_t)cap + i], vy = lo[3 * (size_t)cap + i],
@@ -131,80 +132,37 @@ gap_route_kernel(const double *__restrict__ lo, int cap, int n, double e0, doubl
     r = buf + (size_t)slot * 5;
   } else {
     r = movers + (size_t)atomicAdd(counts + 0, 1) * 5;   // n <= mover_cap: always fits
+    if (cur) {
+      constexpr int NS = ORDER + 1;
+      double xs = x + dp.offx, ys = y + dp.offy;
+      if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+      int ix, iy;
+      double wx[NS], wy[NS];
+      particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+      single_particle_emit<NS>(wx, wy, ix, iy, vx + dp.S * (y * g.dy + g.y0), vy, vz, cur, g);
+    }
   }
   r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
 }
 
-// ---- insertion of movers / arrivals ---------------------------------------------------
-// rows whose x carries this bit pattern are padding of the mover list (unused tail of a
-// warp's slot reservation) and are skipped
-#define GAP_PAD_BITS 0x7ff8dead0badf00dLL
-#define GAP_MCHUNK 64
-
-// One slot claim per warp and destination cell (rows arrive roughly ordered by source
-// tile, so a warp sees few distinct cells and its writes into one cell are contiguous).
-#define GAP_INS_ITEMS 4
-// Insert rows i0 + t*256 (t < GAP_INS_ITEMS, < n) into their cells; a warp-collective:
-// all 32 lanes of a warp call it together.  GAP_INS_ITEMS independent rows per thread:
-// the row load -> slot claim -> store chains overlap instead of adding up.
-__device__ __forceinline__ void gap_insert_rows(const double *__restrict__ rows, int n, int i0,
-                                                skb_particles_t P,
-                                                const int *__restrict__ gap_start,
-                                                int *gap_count, const KeyParams &kp,
-                                                double *leftover, int leftover_cap,
-                                                int *counts) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  double r0[GAP_INS_ITEMS], r1[GAP_INS_ITEMS], r2[GAP_INS_ITEMS], r3[GAP_INS_ITEMS],
-      r4[GAP_INS_ITEMS];
-  bool valid[GAP_INS_ITEMS];
-#pragma unroll
-  for (int t = 0; t < GAP_INS_ITEMS; t++) {
-    const int i = i0 + t * 256;
-    valid[t] = i < n;
-    r0[t] = r1[t] = r2[t] = r3[t] = r4[t] = 0.0;
-    if (valid[t]) {
-      const double *r = rows + (size_t)i * 5;
-      r0[t] = r[0]; r1[t] = r[1]; r2[t] = r[2]; r3[t] = r[3]; r4[t] = r[4];
-    }
-  }
-  int s[GAP_INS_ITEMS], cap[GAP_INS_ITEMS], base[GAP_INS_ITEMS], rank[GAP_INS_ITEMS],
-      leader[GAP_INS_ITEMS];
-#pragma unroll
-  for (int t = 0; t < GAP_INS_ITEMS; t++) {
-    valid[t] = valid[t] && __double_as_longlong(r0[t]) != GAP_PAD_BITS;
-    const int key = valid[t] ? cell_key(r0[t], r1[t], kp) : -1 - lane;
-    const unsigned peers = __match_any_sync(SKB_FULL, key);
-    const int cnt = __popc(peers);
-    leader[t] = __ffs(peers) - 1; rank[t] = __popc(peers & lt);
-    s[t] = cap[t] = base[t] = 0;
-    if (valid[t] && lane == leader[t]) {
-      base[t] = atomicAdd(gap_count + key, cnt);
-      s[t] = gap_start[key]; cap[t] = gap_start[key + 1] - s[t];
-      const int over = min(max(base[t] + cnt - cap[t], 0), cnt);
-      if (over) atomicSub(gap_count + key, over);  // cell full: those go to the leftovers
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < GAP_INS_ITEMS; t++) {
-    const int ss = __shfl_sync(SKB_FULL, s[t], leader[t]);
-    const int cc = __shfl_sync(SKB_FULL, cap[t], leader[t]);
-    const int slot = __shfl_sync(SKB_FULL, base[t], leader[t]) + rank[t];
-    if (!valid[t]) continue;
-    if (slot < cc) {
-      const long long d = (long long)ss + slot;
-      P.x[d] = r0[t]; P.y[d] = r1[t]; P.vx[d] = r2[t]; P.vy[d] = r3[t]; P.vz[d] = r4[t];
-    } else {
-      const int l = atomicAdd(counts + 0, 1);
-      if (l < leftover_cap) {
-        const size_t lc = (size_t)leftover_cap;
-        leftover[l] = r0[t]; leftover[lc + l] = r1[t]; leftover[2 * lc + l] = r2[t];
-        leftover[3 * lc + l] = r3[t]; leftover[4 * lc + l] = r4[t];
-      } else {
-        counts[1] = 1;                            // even the leftover list is full
-      }
-    }
-  }
+// deposit of AoS rows (arrivals from the neighbour ranks) with HBM atomics:
+// deposit_particle_cic/tsc, deposit.pxd:3-118
+template <int ORDER>
+__global__ void __launch_bounds__(256)
+gap_deposit_rows_kernel(const double *__restrict__ rows, int n, double *cur, DepParams dp,
+                        DevGrid g) {
+  constexpr int NS = ORDER + 1;
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double *r = rows + (size_t)i * 5;
+  if (__double_as_longlong(r[0]) == GAP_PAD_BITS) return;
+  double xs = r[0] + dp.offx, ys = r[1] + dp.offy;
+  if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+  int ix, iy;
+  double wx[NS], wy[NS];
+  particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+  single_particle_emit<NS>(wx, wy, ix, iy, r[2] + dp.S * (r[1] * g.dy + g.y0), r[3], r[4],
+                           cur, g);
 }
 
 __global__ void __launch_bounds__(256)
@@ -216,39 +174,6 @@ gap_insert_kernel(const double *__restrict__ rows, int n, skb_particles_t P,
 }
 
 // ---- push on the gapped layout -----------------------------------------------------------
-struct GapPush {
-  KickParams k;
-  double dtdsx, dtdsy, vx_boost, x_boost;
-  int flags;                 // SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X
-  KeyParams key;
-  int *gap_count;            // updated in place
-  double *movers;            // AoS rows
-  int mover_cap;
-  double *sbufl, *sbufr;
-  int nbmax, rank, nvp;
-  int *counts;               // [0] movers, [1] sbufl, [2] sbufr, [3] flags (1: mover list
-                             // full -> some particles sit in the wrong cell, 2: nbmax),
-                             // [4] movers re-inserted by their own block
-  // movers whose new cell belongs to the same CTA are parked in a scratch block (claimed
-  // from a pool for the lifetime of the CTA, L2 resident) and dropped into their cells
-  // by the CTA itself once all its cells are compacted
-  double *scratch;           // [npool][scratch_rows][5]
-  int scratch_rows, npool;
-  int *pool_owner;           // [npool] 0 = free
-  const int *gap_start;
-  double *leftover;          // SoA [5][leftover_cap]: rows whose cell is full
-  int leftover_cap;
-  int *lcounts;              // [0] leftover rows, [1] leftover overflow
-};
-
-// fused push_and_deposit on the gapped layout (push_and_deposit.pyx:10-170): sources
-// grid, deposit offsets / shear, half-step drift factors
-struct GapDeposit {
-  double *cur;
-  DepParams dp;
-  double d2x, d2y;           // 0.5*dt/dx, 0.5*dt/dy, push_and_deposit.pyx:37-38
-};
-
 // PD = 0: push (push / push_modified + boundary epilogue)
 // PD = 1: push_and_deposit, update = True   (gather at the old position, kick, half
 //         drift, deposit, second half drift, x wrap, then the same routing as PD = 0)
@@ -596,7 +521,13 @@ extern "C" int skb_gap_insert(const double *rows, int n, skb_particles_t p,
   return 0;
 }
 
-// pd: 0 = push, 1 = push_and_deposit with update, 2 = push_and_deposit without update
+size_t cell_stream_smem(int pd);
+int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const double *E,
+                       const double *B, const DevGrid &g, const GapPush &q,
+                       const GapDeposit &dq, int ntiles, cudaStream_t st);
+
+// pd: 0 = push, 1 = push_and_deposit with update, 2 = push_and_deposit without update,
+// 3 = push + the full-step deposit that follows it (sources.py:27-50), raw sums
 static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double *B,
                         const skb_grid_t *grid, int order, double qtmh, double dt,
                         int modified, double Omega, double S, int epi_flags, double epi_S,
@@ -624,19 +555,26 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
   q.gap_count = gap_count; q.movers = movers; q.mover_cap = mover_cap;
   q.sbufl = sbufl; q.sbufr = sbufr; q.nbmax = nbmax; q.rank = rank; q.nvp = nvp;
   q.counts = counts;
-  q.scratch = scratch; q.scratch_rows = scratch_rows;
-  q.npool = (pd != 2 && scratch && pool_owner && scratch_rows > 0) ? npool : 0;
+  q.scratch = scratch; q.scratch_rows = scratch_rows & ~1;   // even: 16-byte rows for TMA
+  q.npool = (pd != 2 && scratch && pool_owner && scratch_rows > 1) ? npool : 0;
   q.pool_owner = pool_owner; q.gap_start = gap_start;
   q.leftover = leftover; q.leftover_cap = leftover_cap; q.lcounts = leftover_counts;
   GapDeposit dq = {};
   dq.cur = current;
   dq.dp.offx = q.k.offEx;                          // offsetE reused, push_and_deposit.pyx:71
   dq.dp.offy = q.k.offEy;
+  if (pd == 3) {                                   // deposit.pyx:14-15
+    dq.dp.offx = q.key.offx;
+    dq.dp.offy = q.key.offy;
+  }
   dq.dp.S = dep_S;
   dq.d2x = 0.5 * dt / g.dx;
   dq.d2y = 0.5 * dt / g.dy;
-  // more blocks than CTAs can ever be resident, or the claim loop could spin forever
-  if (q.npool > 0 && q.npool < 148 * 4) return (int)cudaErrorInvalidValue;
+  // the cell-stream kernel (cellstream.cu) serves push and push + deposit on 16 x 16
+  // tiles; SKB_GAP_GENERIC=1 keeps the generic kernel below (A/B measurements)
+  static const bool force_generic = getenv("SKB_GAP_GENERIC") && atoi(getenv("SKB_GAP_GENERIC"));
+  const bool stream_kernel = (pd == 0 || pd == 3) && tlx == 4 && tly == 4 && !force_generic;
+  if (pd == 3 && !stream_kernel) return (int)cudaErrorNotSupported;
   cudaError_t e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (q.npool > 0) {       // (all blocks free: a failed earlier launch cannot leave claims)
@@ -662,8 +600,9 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
         (uintptr_t)p.vz) & 15) != 0)
     return (int)cudaErrorMisalignedAddress;
   void (*k)(skb_particles_t, const double *, const double *, DevGrid, DevTiling, GapPush,
-            GapDeposit, int, int, int);
-  if (pd == 0) {
+            GapDeposit, int, int, int) = nullptr;
+  if (stream_kernel) {
+  } else if (pd == 0) {
     if (order == 1) k = modified ? push_gapped_kernel<1, true, 0> : push_gapped_kernel<1, false, 0>;
     else k = modified ? push_gapped_kernel<2, true, 0> : push_gapped_kernel<2, false, 0>;
   } else if (pd == 1) {
@@ -671,11 +610,26 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
   } else {
     k = order == 1 ? push_gapped_kernel<1, false, 2> : push_gapped_kernel<2, false, 2>;
   }
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  if (!stream_kernel) {
+    // the scratch-pool claim spins until a block is free: the pool must hold at least as
+    // many blocks as CTAs can be resident
+    if (q.npool > 0) {
+      int dev = 0, sms = 0, per = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+      }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, GAP_THREADS, smem);
+      if (e != cudaSuccess) return (int)e;
+      if (q.npool < max(per, 1) * max(sms, 1)) return (int)cudaErrorInvalidValue;
+    } else if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
   }
-  if (pd) {                // in-band flag of the generic kernel below (ihole[0] = -1)
+  if (pd == 1 || pd == 2) {  // in-band flag of the generic kernel below (ihole[0] = -1)
     e = cudaMemsetAsync(ihole, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
   }
@@ -687,7 +641,7 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
     skb_particles_t lp = {leftover, leftover + lc, leftover + 2 * lc, leftover + 3 * lc,
                           leftover + 4 * lc};
     int rc;
-    if (pd) {
+    if (pd == 1 || pd == 2) {
       if (nleft > ntmax) return (int)cudaErrorInvalidValue;
       rc = skb_push_and_deposit(lp, nleft, E, B, grid, order, qtmh, dt, ihole, ntmax, current,
                                 dep_S, pd == 1, nullptr, nullptr, tlx, tly, stream);
@@ -700,9 +654,15 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
     }
     if (rc) return rc;
     if (pd != 2) {
-      gap_route_kernel<<<(nleft + 255) / 256, 256, 0, st>>>(
-          leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
-          sbufr, nbmax, counts);
+      double *rc_cur = pd == 3 ? current : nullptr;
+      if (order == 1)
+        gap_route_kernel<1><<<(nleft + 255) / 256, 256, 0, st>>>(
+            leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
+            sbufr, nbmax, counts, rc_cur, dq.dp, g);
+      else
+        gap_route_kernel<2><<<(nleft + 255) / 256, 256, 0, st>>>(
+            leftover, leftover_cap, nleft, g.e0, g.e1, (double)g.ny, rank, nvp, movers, sbufl,
+            sbufr, nbmax, counts, rc_cur, dq.dp, g);
       SKB_CHECK_LAUNCH();
     }
   }
@@ -712,6 +672,8 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
     e = cudaMemsetAsync(leftover_counts, 0, 2 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
   }
+  if (stream_kernel)
+    return cell_stream_launch(pd, order, modified, p, E, B, g, q, dq, ntiles, st);
   k<<<ntiles * parts, GAP_THREADS, smem, st>>>(p, E, B, g, tl, q, dq, parts, ws, wr);
   SKB_CHECK_LAUNCH();
   return 0;
@@ -746,4 +708,43 @@ extern "C" int skb_push_and_deposit_gapped(
                       gap_start, gap_count, movers, mover_cap, sbufl, sbufr, nbmax, counts,
                       rank, nvp, leftover, leftover_cap, nleft, leftover_counts, scratch,
                       scratch_rows, npool, pool_owner, stream);
+}
+
+// push / push_modified + the full-step deposit that follows it in the time loop
+// (particles.py:159-188 then sources.py:27-50, deposit.pyx:6-34), one sweep: `current`
+// receives the raw stencil sums of every particle that is in the slab after the push
+// (arrivals from the neighbour ranks: skb_deposit_rows).  counts[3] & 16: some rows
+// bypassed the fused deposit (scratch block full) - redo it with skb_deposit.
+extern "C" int skb_push_deposit_gapped(
+    skb_particles_t p, const double *E, const double *B, const skb_grid_t *grid, int order,
+    double qtmh, double dt, int modified, double Omega, double S, int epi_flags, double epi_S,
+    double epi_t, double *current, double dep_S, int tlx, int tly, const int *gap_start,
+    int *gap_count, double *movers, int mover_cap, double *sbufl, double *sbufr, int nbmax,
+    int *counts, int rank, int nvp, double *leftover, int leftover_cap, int nleft,
+    int *leftover_counts, double *scratch, int scratch_rows, int npool, int *pool_owner,
+    void *stream) {
+  return gapped_sweep(3, p, E, B, grid, order, qtmh, dt, modified, Omega, S, epi_flags, epi_S,
+                      epi_t, current, dep_S, nullptr, 0, tlx, tly, gap_start, gap_count,
+                      movers, mover_cap, sbufl, sbufr, nbmax, counts, rank, nvp, leftover,
+                      leftover_cap, nleft, leftover_counts, scratch, scratch_rows, npool,
+                      pool_owner, stream);
+}
+
+// deposit_cic/tsc (deposit.pyx:6,21) of n AoS rows {x, y, vx, vy, vz} (e.g. the arrivals
+// of a migration step) into `current`, HBM atomics
+extern "C" int skb_deposit_rows(const double *rows, int n, double *current,
+                                const skb_grid_t *grid, int order, double S, void *stream) {
+  if (n <= 0) return 0;
+  if (order != 1 && order != 2) return (int)cudaErrorInvalidValue;
+  DevGrid g = make_grid(grid);
+  DepParams dp;
+  dp.offx = g.lbx - 0.5;              // deposit.pyx:14-15
+  dp.offy = g.lby - 0.5 - g.noff;
+  dp.S = S;
+  if (order == 1)
+    gap_deposit_rows_kernel<1><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, n, current, dp, g);
+  else
+    gap_deposit_rows_kernel<2><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, n, current, dp, g);
+  SKB_CHECK_LAUNCH();
+  return 0;
 }

@@ -105,6 +105,30 @@ static inline KickParams make_kick(const DevGrid &g, double qtmh, double dt,
   return k;
 }
 
+// rescale (particle_push.pxd:93-97), [rotation / shear terms, particle_push.pyx:75-76],
+// Boris kick (kick_particle, particle_push.pxd:69-86).  `y` is the position BEFORE the
+// drift.
+template <bool MODIFIED>
+__device__ __forceinline__ void rescale_and_kick(double (&e)[3], double (&b)[3],
+                                                 const DevGrid &g, const KickParams &q,
+                                                 double y, double &vx, double &vy,
+                                                 double &vz) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { e[k] = e[k] * q.qtmh; b[k] = b[k] * q.qtmh; }
+  if (MODIFIED) {  // particle_push.pyx:75-76
+    b[2] = b[2] + q.Omega * q.dt;
+    e[1] = e[1] - q.S * (g.y0 + y * g.dy) * b[2];
+  }
+  const double vmx = vx + e[0], vmy = vy + e[1], vmz = vz + e[2];
+  const double vpx = vmx + (vmy * b[2] - vmz * b[1]);
+  const double vpy = vmy + (vmz * b[0] - vmx * b[2]);
+  const double vpz = vmz + (vmx * b[1] - vmy * b[0]);
+  const double fac = 2. / (1. + b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+  vx = vmx + fac * (vpy * b[2] - vpz * b[1]) + e[0];
+  vy = vmy + fac * (vpz * b[0] - vpx * b[2]) + e[1];
+  vz = vmz + fac * (vpx * b[1] - vpy * b[0]) + e[2];
+}
+
 // gather E and B at (x, y), rescale, [rotation/shear terms], Boris kick.
 // particle_push.pyx:28-36 (+ :75-76) and kick_particle, particle_push.pxd:69-86
 template <int ORDER, bool MODIFIED>
@@ -122,19 +146,5 @@ __device__ __forceinline__ void fields_and_kick(const double *sE, const double *
     gather_tsc(sE, w, ws, E, g, x + q.offEx, y + q.offEy, e);
     gather_tsc(sB, w, ws, B, g, x + q.offBx, y + q.offBy, b);
   }
-  // rescale, particle_push.pxd:93-97
-#pragma unroll
-  for (int k = 0; k < 3; k++) { e[k] = e[k] * q.qtmh; b[k] = b[k] * q.qtmh; }
-  if (MODIFIED) {  // particle_push.pyx:75-76
-    b[2] = b[2] + q.Omega * q.dt;
-    e[1] = e[1] - q.S * (g.y0 + y * g.dy) * b[2];
-  }
-  const double vmx = vx + e[0], vmy = vy + e[1], vmz = vz + e[2];
-  const double vpx = vmx + (vmy * b[2] - vmz * b[1]);
-  const double vpy = vmy + (vmz * b[0] - vmx * b[2]);
-  const double vpz = vmz + (vmx * b[1] - vmy * b[0]);
-  const double fac = 2. / (1. + b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
-  vx = vmx + fac * (vpy * b[2] - vpz * b[1]) + e[0];
-  vy = vmy + fac * (vpz * b[0] - vpx * b[2]) + e[1];
-  vz = vmz + fac * (vpx * b[1] - vpy * b[0]) + e[2];
+  rescale_and_kick<MODIFIED>(e, b, g, q, y, vx, vy, vz);
 }

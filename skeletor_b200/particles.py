@@ -157,8 +157,28 @@ class Particles:
         # gapped layout (see _push_gapped): particles stay ordered without a full move
         # pass.  Needs Nmax >= ~1.3 N; push()/push_modified() fall back to the dense
         # path when the slot ranges do not fit.
-        self.gapped = os.environ.get("SKELETOR_B200_GAPPED", "0") == "1"
+        # On by default (SKELETOR_B200_GAPPED=0 turns it off): instances whose slot ranges
+        # do not fit (Nmax < ~1.3 N) or that are converted back after every push (code
+        # that reads the particles each step) stay on / return to the dense path.
+        self.gapped = os.environ.get("SKELETOR_B200_GAPPED", "1") != "0"
         self.gapped_push_and_deposit = True   # (only with gapped) fused sweep on that layout
+        # push + the full-step deposit that follows it in ONE sweep (skb_push_deposit_gapped):
+        # the push also accumulates the stencil sums of the new positions into a private
+        # grid and Sources.deposit(ions) picks that grid up when the particles have not
+        # been touched in between.  "auto": switched on by the first deposit that follows a
+        # push, switched off again when a fused result goes unused.
+        self.fuse_deposit = os.environ.get("SKELETOR_B200_FUSE", "auto")
+        if self.fuse_deposit in ("0", "1"):
+            self.fuse_deposit = self.fuse_deposit == "1"
+        self._fuse_next = False
+        self._fused_grid = None
+        self._fused_valid = False
+        self._fused_used = False
+        self._fused_S = 0.0
+        self._last_op = None
+        self._gap_fail = None         # N at which the slot ranges did not fit
+        self._gap_thrash = 0          # gapped -> dense conversions after a single push
+        self._gap_pushes = 0
         self.mover_fraction = 0.1     # size of the global mover list relative to Nmax
         self._rep = "dense"
         self._gap_start = None
@@ -175,6 +195,7 @@ class Particles:
     def N(self, n):
         if getattr(self, "_rep", "dense") == "gapped":
             self._dense()              # "the first N entries" only means something there
+        self._fused_valid = False
         self._N = int(n)
         self._N_global = None          # unknown until the next reduction
 
@@ -204,6 +225,8 @@ class Particles:
 
     def _touched(self):
         self._sorted = False
+        self._fused_valid = False
+        self._last_op = None
 
     def __getitem__(self, key):
         self._dense()
@@ -323,7 +346,7 @@ class Particles:
             # scratch blocks for the movers a thread block re-inserts itself: sized for
             # ~3x the expected in-block movers of a uniform plasma
             ncta = max(ntiles, min(2368, 32*ntiles))
-            self._scr_rows = int(min(max(1024, 0.5*self.size/ncta), 1 << 16))
+            self._scr_rows = int(min(max(1024, 0.5*self.size/ncta), 1 << 16)) & ~1
             self._npool = 1024
             self._scratch = torch.zeros((self._npool, self._scr_rows, 5), **f64)
             self._pool_owner = torch.zeros(self._npool, **i32)
@@ -335,6 +358,16 @@ class Particles:
             return False
         if self.size % 2:
             return False        # rows of the [5][Nmax] tensor must be 16-byte aligned
+        if self._gap_fail is not None and \
+                abs(self.N - self._gap_fail) <= 0.02*self._gap_fail:
+            return False        # did not fit last time and N has hardly changed
+        if self._gap_thrash >= 4:
+            # the caller reads the particles after every push: converting back and forth
+            # costs more than the tile sort; try again every 64 pushes
+            self._gap_thrash += 1
+            if self._gap_thrash < 68:
+                return False
+            self._gap_thrash = 0
         if not (self._sorted and self._n_sorted == self.N):
             self.sort()
         self._gap_alloc()
@@ -344,17 +377,24 @@ class Particles:
                   self._block_sums.data_ptr(), self.size, _stream())
         total = int(self._gap_start[-1].item())
         if total > self.size or total < 0:
+            if self._gap_fail is None and self.size >= 1.25*self.N:
+                warn("gapped particle layout needs Nmax >= ~1.36 N at this occupation "
+                     "(N={}, Nmax={}): staying on the dense layout".format(self.N, self.size))
+            self._gap_fail = self.N
             return False
+        self._gap_fail = None
         self._data, self._alt = self._alt, self._data
         self._rep = "gapped"
         self._gap_nleft = 0
         self._gap_dirty = False
+        self._gap_pushes = 0
         return True
 
     def _dense(self):
         """back to the dense representation every other method works on"""
         if self._rep != "gapped":
             return
+        self._gap_thrash = self._gap_thrash + 1 if self._gap_pushes <= 1 else 0
         nleft = self._gap_nleft
         st = _stream()
         _lib.call("skb_gap_densify", self._c, self._soa(self._alt),
@@ -386,17 +426,44 @@ class Particles:
         tile sort -> skb_gap_build)."""
         if self._rep != "gapped" and not self._to_gapped():
             return False
-        self._gap_finish(self._gap_kernel(E, B, dt, modified))
+        fuse = self.fuse_deposit is True or \
+            (self.fuse_deposit == "auto" and self._fuse_next)
+        self._gap_finish(self._gap_kernel(E, B, dt, modified, fuse), fused=fuse)
+        self._gap_pushes += 1
         return True
 
-    def _gap_kernel(self, E, B, dt, modified):
+    def _fused_sources(self):
+        """private grid of the fused push + deposit sweep (raw sums, [myp][mx][4])"""
+        if self._fused_grid is None:
+            m = self.manifold
+            self._fused_grid = torch.zeros((m.myp, m.mx, 4), dtype=torch.float64,
+                                           device=self.device)
+        return self._fused_grid
+
+    def _fused_for(self, sources, S):
+        """the grid Sources.deposit(self) may copy instead of running the deposit kernel:
+        the last push accumulated it and nothing has touched the particles since"""
+        if self._fused_valid and sources.grid is self.manifold and \
+                float(S) == self._fused_S and not self.deterministic:
+            self._fused_used = True
+            return self._fused_grid
+        return None
+
+    def _gap_kernel(self, E, B, dt, modified, fuse=False):
         m = self.manifold
         comm = m.comm
         self.time += dt
         args, flags = self._push_args(dt, modified)
         cnt = self._counts
-        _lib.call("skb_push_gapped", self._c, E.ptr, B.ptr, *args, flags,
-                  float(getattr(m, 'S', 0.0)), float(self.time), TLX, TLY,
+        extra = ()
+        if fuse:
+            fs = self._fused_sources()
+            fs.zero_()
+            self._fused_S = float(getattr(m, 'S', 0.0))
+            extra = (fs.data_ptr(), self._fused_S)
+        _lib.call("skb_push_deposit_gapped" if fuse else "skb_push_gapped",
+                  self._c, E.ptr, B.ptr, *args, flags,
+                  float(getattr(m, 'S', 0.0)), float(self.time), *extra, TLX, TLY,
                   self._gap_start.data_ptr(), self._gap_count.data_ptr(),
                   self._movers.data_ptr(), self._movers.shape[0],
                   self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
@@ -439,7 +506,7 @@ class Particles:
             msg = "ihole overflow error: ntmax={}, ierr={}"
             raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
 
-    def _gap_finish(self, cnt, cfl=False):
+    def _gap_finish(self, cnt, cfl=False, fused=False):
         m = self.manifold
         st = _stream()
         nm, nl, nr, fl, nlocal = cnt[:5].tolist()
@@ -448,7 +515,17 @@ class Particles:
             raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
         if fl & 2:
             raise RuntimeError("particle buffer overflow: nbmax={}".format(self.nbmax))
+        if fl & 8:
+            raise RuntimeError("gapped layout: mover lists overflowed, particles were "
+                               "lost (raise Particles.mover_fraction; {} rows)".format(
+                                   self._movers.shape[0]))
         nkeep = self._exchange(nl, nr)
+        if fused:
+            # the arrivals were not in this slab when the push accumulated its grid
+            _lib.call("skb_deposit_rows", self._keep.data_ptr(), nkeep,
+                      self._fused_grid.data_ptr(), m.c, self.order, self._fused_S, st)
+        self._fused_valid = fused and not (fl & 16)
+        self._fused_used = False
         new_n = self.N - nl - nr + nkeep
         if new_n > self.size:
             self.info[0] = new_n - self.size
@@ -496,6 +573,7 @@ class Particles:
                          vx[ind], vy[ind], vz[ind]])
         self._data[:, :self.N] = torch.as_tensor(host, device=self.device)
         self._sorted = False
+        self._gap_fail = None
 
     def deposit(self, **kwds):
         self.sources.deposit(self, **kwds)
@@ -512,6 +590,7 @@ class Particles:
         """Move particles that left the slab to the neighbouring ranks: ppic2's
         cppmove2 (pplib2.c:607-981) as pack -> NCCL ring exchange -> unpack."""
         self._dense()
+        self._fused_valid = False
         g = self.manifold
         comm = g.comm
         gc = g.c
@@ -624,6 +703,8 @@ class Particles:
     def periodic_x(self):
         """Applies periodic boundaries on particles along x"""
         self._dense()
+        self._fused_valid = False
+        self._last_op = None
         _lib.call("skb_periodic_x", self._c, self.N, self.manifold.c, _stream())
 
     def calculate_ihole(self):
@@ -641,11 +722,17 @@ class Particles:
     def shear_periodic_y(self):
         """Shearing periodic boundaries along y (particles.py:145-157)."""
         self._dense()
+        self._fused_valid = False
+        self._last_op = None
         _lib.call("skb_shear_periodic_y", self._c, self.N, self.manifold.c,
                   float(self.manifold.S), float(self.time), _stream())
         self.periodic_y()
 
     def _push(self, E, B, dt, modified):
+        if self._fused_valid and not self._fused_used:
+            self._fuse_next = False        # the last fused deposit was not picked up
+        self._fused_valid = False
+        self._last_op = "push"
         if self.gapped and self.order in (1, 2) and \
                 self._push_gapped(E, B, dt, modified):
             return
@@ -747,6 +834,24 @@ class Particles:
                   self._tiling_c(), self._epilogue(flags, getattr(m, 'S', 0.0)),
                   _stream())
 
+    def kick(self, E, B, dt):
+        """Velocity update alone: gather E, B at the particles and apply the Boris kick
+        of `push` (kick_particle, particle_push.pxd:69-86) over dt; positions, time and
+        slab membership do not change.  (The reference has no public kick - only the
+        inlined cdef reachable through push - this is push without drift and boundary
+        conditions: the same kernel with a zero drift factor.)"""
+        if self.order not in (1, 2):
+            msg = 'Interpolation order {} not implemented.'
+            raise RuntimeError(msg.format(self.order))
+        self._dense()
+        self._fused_valid = False
+        self._last_op = None
+        qtmh = self.charge/self.mass*dt/2
+        self._ensure_sorted()
+        _lib.call("skb_boris_push", self._c, self.N, E.ptr, B.ptr, self.manifold.c,
+                  self.order, float(qtmh), 0.0, 0, 0.0, 0.0, self._tiling_c(),
+                  self._epilogue(0), _stream())
+
     def push(self, E, B, dt):
         """A standard Boris push which updates positions and velocities
         (particles.py:159-188).  If shear is turned on, E needs to be E_star and B
@@ -764,6 +869,8 @@ class Particles:
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
+        self._fused_valid = False
+        self._last_op = None
         if self.gapped and self.gapped_push_and_deposit and \
                 (self._rep == "gapped" or self._to_gapped()) and \
                 self._gap_nleft < self.ntmax - 1:
@@ -806,6 +913,8 @@ class Particles:
     def drift(self, dt):
         """particles.py:259-265: drift, then periodic_x and periodic_y"""
         self._dense()
+        self._fused_valid = False
+        self._last_op = None
         flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X
         _lib.call("skb_drift", self._c, self.N, float(dt), self.manifold.c,
                   self._epilogue(flags), _stream())

@@ -34,10 +34,25 @@ class Sources(Field):
         if particles.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(particles.order))
-        if erase:
-            self.t.zero_()
         # Rate of shear
         S = getattr(self.grid, 'S', 0.0)
+        if particles.fuse_deposit == "auto" and particles._last_op == "push":
+            particles._fuse_next = True    # deposit follows push: fuse the next pair
+        particles._last_op = "deposit"
+        fused = particles._fused_for(self, S)
+        if fused is not None:
+            # the push already accumulated these sums (skb_push_deposit_gapped)
+            if erase:
+                self.t.copy_(fused)
+            else:
+                self.t.add_(fused)
+            self.boundaries_set = False
+            self.normalize(particles)
+            if set_boundaries:
+                self.set_boundaries()
+            return
+        if erase:
+            self.t.zero_()
         if particles.deterministic:
             particles._dense()         # the fixed-order deposit needs the dense ordering
         particles._ensure_sorted()

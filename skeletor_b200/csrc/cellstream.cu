@@ -9,9 +9,12 @@
 //
 //  * one warp streams the particles of one ROW of 16 cells of a 16 x 16 tile; a CTA of 8
 //    warps owns half a tile and stages its own (8+5) x (16+5) window of E and B;
-//  * particles arrive through a per-warp ring of 64-particle stages filled by TMA 1-D bulk
-//    copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx): lanes 0..4
-//    issue ONE copy each (x, y, vx, vy, vz), nobody computes per-lane load addresses;
+//  * particles arrive through a per-warp ring of 64-particle stages, each filled by ONE
+//    TMA tensor copy (cp.async.bulk.tensor.2d + mbarrier complete_tx) of a [5 rows x 64
+//    slots] box of the [5][Nmax] particle tensor - one elected lane issues it, nobody
+//    computes per-lane load addresses; a stage is processed as two particles per lane, so
+//    every lane carries two independent dependency chains (4 warps per scheduler are too
+//    few to hide the fp64 / shared-memory latencies otherwise);
 //  * all particles of a cell share the E stencil (the sort key IS the E-gather / deposit
 //    base cell), so for CIC the 2 x 2 x 3 E values live in registers for the whole cell;
 //    B is read per lane from the shared window (its base cell differs by the half-cell
@@ -30,6 +33,7 @@
 // Per-particle arithmetic keeps the reference's operation order (-fmad=false), so the
 // results are bit-identical to push_gapped_kernel / the oracle.
 #include <cstdlib>
+#include <cuda.h>
 #include "gapped.cuh"
 
 #define CS_THREADS 256
@@ -74,13 +78,13 @@ __device__ __forceinline__ bool cs_mbar_try_wait(unsigned bar, unsigned parity) 
       : "memory");
   return ok != 0;
 }
-// global -> shared, completion signalled on the mbarrier (bytes: multiple of 16; both
-// addresses 16-byte aligned)
-__device__ __forceinline__ void cs_bulk_load(unsigned dst, const void *src, unsigned bytes,
-                                             unsigned bar) {
+// box of a 2-D tensor (global) -> shared, completion signalled on the mbarrier; c0 = slot
+// (inner coordinate), c1 = row
+__device__ __forceinline__ void cs_tma_load_2d(unsigned dst, const CUtensorMap *tm, int c0,
+                                               int c1, unsigned bar) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 // shared -> global, tracked by the issuing thread's bulk async-group
@@ -183,7 +187,21 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
           double *o = q.movers + (size_t)ms * 5;
           o[0] = r0[t]; o[1] = r1[t]; o[2] = r2[t]; o[3] = r3[t]; o[4] = r4[t];
         } else {
-          atomicOr(q.counts + 3, 8);                // list full: the particle is lost
+          // list full: park the row in whichever of this CTA's cells has a free slot
+          // (flag 1: some particles sit in a wrong cell, the layout gets rebuilt)
+          for (int a = 0; a < CS_CELLS && !placed; a++) {
+            const int c = c0 + (((unsigned)key[t] + (unsigned)a) & (CS_CELLS - 1));
+            const int cs = q.gap_start[c], cc2 = q.gap_start[c + 1] - cs;
+            const int pos = atomicAdd(q.gap_count + c, 1);
+            if (pos < cc2) {
+              const long long d = (long long)cs + pos;
+              P.x[d] = r0[t]; P.y[d] = r1[t]; P.vx[d] = r2[t]; P.vy[d] = r3[t]; P.vz[d] = r4[t];
+              placed = true;
+            } else {
+              atomicSub(q.gap_count + c, 1);
+            }
+          }
+          atomicOr(q.counts + 3, placed ? 1 : 8);   // 8: no room anywhere, particle lost
         }
       }
     }
@@ -202,57 +220,334 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
 }
 
 // Reserve room for 32 mover rows (one half of a warp's buffer): in the CTA's scratch block
-// if it has room, else on the global mover list (rows there bypass phase B: with PD the
-// caller redoes the deposit, flag 16).  Returns NULL when both are full: the warp then
-// parks its movers in their old cells (flag 1: the layout is rebuilt).  Every reservation
-// that succeeds is later written in full (rows or padding).  Warp-collective.
+// if it has room (returns the row), else on the global mover list (returns CS_GLOBAL | row;
+// rows there bypass phase B: with PD the caller redoes the deposit, flag 16).  CS_NOSLOT
+// when both are full: the warp then parks its movers in their old cells (flag 1: the
+// layout is rebuilt).  Every reservation that succeeds is later written in full (rows or
+// padding).  Warp-collective.
+#define CS_NOSLOT (-1)
+#define CS_GLOBAL (1 << 30)
 template <int PD>
-__device__ __forceinline__ double *cs_reserve(int *s_nrows, double *scr, int scr_rows,
-                                              const GapPush &q) {
+__device__ __noinline__ int cs_reserve(int *s_nrows, int scr_rows, int *counts, double *movers,
+                                       int mover_cap) {
   const int lane = threadIdx.x & 31;
   int slot = 0;
   if (lane == 0) slot = atomicAdd(s_nrows, 32);
   slot = __shfl_sync(SKB_FULL, slot, 0);
-  if (slot + 32 <= scr_rows) return scr + (size_t)slot * 5;
+  if (slot + 32 <= scr_rows) return slot;
   // 33 rows: the list head may be odd (leftover rows), a TMA store needs 16-byte rows
   int gs = 0;
-  if (lane == 0) gs = atomicAdd(q.counts + 0, 33);
+  if (lane == 0) gs = atomicAdd(counts + 0, 33);
   gs = __shfl_sync(SKB_FULL, gs, 0);
-  if (gs + 33 <= q.mover_cap) {
+  if (gs + 33 <= mover_cap) {
     const int ge = (gs + 1) & ~1;
     if (lane == 0) {
-      q.movers[(size_t)(gs == ge ? gs + 32 : gs) * 5] = __longlong_as_double(GAP_PAD_BITS);
-      if (PD != 0) atomicOr(q.counts + 3, 16);
+      movers[(size_t)(gs == ge ? gs + 32 : gs) * 5] = __longlong_as_double(GAP_PAD_BITS);
+      if (PD != 0) atomicOr(counts + 3, 16);
     }
-    return q.movers + (size_t)ge * 5;
+    return CS_GLOBAL | ge;
   }
   // no room: whatever part of the reservation lies inside the list becomes padding
-  for (int r = gs + lane; r < min(gs + 33, q.mover_cap); r += 32)
-    q.movers[(size_t)r * 5] = __longlong_as_double(GAP_PAD_BITS);
-  if (lane == 0) atomicOr(q.counts + 3, 1);
-  return nullptr;
+  for (int r = gs + lane; r < min(gs + 33, mover_cap); r += 32)
+    movers[(size_t)r * 5] = __longlong_as_double(GAP_PAD_BITS);
+  if (lane == 0) atomicOr(counts + 3, 1);
+  return CS_NOSLOT;
+}
+
+// per-warp state of the mover staging
+struct CsMovers {
+  int count;      // rows staged so far by this warp
+  int slot;       // reservation of the half being filled (CS_NOSLOT: lists full, park)
+};
+
+// Stage the movers of one ballot (<= 32 rows) as AoS rows in the warp's buffer; a half (32
+// rows, 1280 B) that fills up goes out with one TMA bulk store to the destination that
+// was reserved BEFORE its first row was staged.  Returns true for the lanes whose
+// particle could not be staged (lists full): it stays in its old cell.  Warp-collective.
+template <int PD>
+__device__ __forceinline__ bool cs_stage_movers(bool mover, double x, double y, double vx,
+                                                double vy, double vz, CsMovers &mv,
+                                                double *mbuf, int *s_nrows, double *scr,
+                                                int scr_rows, const GapPush &q) {
+  const unsigned mm = __ballot_sync(SKB_FULL, mover);
+  if (mm == 0) return false;
+  if (mv.slot == CS_NOSLOT) return mover;            // parking
+  const int lane = threadIdx.x & 31;
+  const int pos = mv.count + __popc(mm & ((1u << lane) - 1u));
+  const int after = mv.count + __popc(mm);
+  const int boundary = (mv.count | 31) + 1;
+  bool parked = false;
+  if (after < boundary) {                             // the common case: no half completes
+    if (mover) {
+      double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
+      r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+    }
+    mv.count = after;
+    return false;
+  }
+  // this ballot completes a half: the half about to be entered must have been read out
+  if (lane == 0) cs_bulk_wait_read();
+  __syncwarp();
+  const int nxt = cs_reserve<PD>(s_nrows, scr_rows, q.counts, q.movers, q.mover_cap);
+  if (mover) {
+    if (nxt == CS_NOSLOT && pos >= boundary) {
+      parked = true;
+    } else {
+      double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
+      r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+    }
+  }
+  const int h = (mv.count >> 5) & 1;                  // the half that is complete now
+  cs_fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    double *dst = (mv.slot & CS_GLOBAL) ? q.movers + (size_t)(mv.slot & ~CS_GLOBAL) * 5
+                                        : scr + (size_t)mv.slot * 5;
+    cs_bulk_store(dst, cs_smem(mbuf + h * 160), 1280u);
+  }
+  mv.slot = nxt;
+  mv.count = nxt == CS_NOSLOT ? boundary : after;
+  return parked;
+}
+
+// ---- per-particle work of one block of NP x 32 particles of a cell ------------------------
+template <int ORDER, int PD>
+struct CsCell {
+  int cix, ciy, s, wcur;          // cell coordinates, first slot, stayers written so far
+  bool fast;                      // every stencil of this cell lies inside the window
+  double eC[4][3];                // (CIC) the E stencil of the cell
+  double xsafe, ysafe;            // a position inside the cell for idle lanes
+  Acc<ORDER + 1> acc;             // (PD) stencil sums of the cell
+};
+
+template <int ORDER, bool MODIFIED, int PD, int NP>
+__device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
+                                         CsCell<ORDER, PD> &c, CsMovers &mv,
+                                         skb_particles_t P, long long pstride,
+                                         const double *sE, const double *sB, double *sS,
+                                         const Window &w, const double *E, const double *B,
+                                         const DevGrid &g, const GapPush &q,
+                                         const GapDeposit &dq, double *mbuf, int *s_nrows,
+                                         double *scr, int scr_rows) {
+  constexpr int NS = ORDER + 1;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const double nxd = (double)g.nx, nyd = (double)g.ny;
+  bool act[NP];
+  double x[NP], y[NP], vx[NP], vy[NP], vz[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    act[p] = p * 32 + lane < nact;
+    // idle lanes compute on a harmless particle at rest inside the cell
+    x[p] = c.xsafe; y[p] = c.ysafe; vx[p] = vy[p] = vz[p] = 0.0;
+    if (act[p]) {
+      const double *r = pp + p * 32;
+      x[p] = r[0]; y[p] = r[pitch]; vx[p] = r[2 * pitch]; vy[p] = r[3 * pitch];
+      vz[p] = r[4 * pitch];
+    }
+  }
+  // ---- gather + kick.  The cell promises the E base cell of its particles (the sort key)
+  // and with it the B base cell up to + 1 (xb = xe + 1/2 before rounding, rounding is
+  // monotonic); a lane that breaks the promise sends the warp down the generic path.
+  double xe[NP], ye[NP], xb[NP], yb[NP];
+  int ixe[NP], iye[NP], ixb[NP], iyb[NP];
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    xe[p] = x[p] + q.k.offEx; ye[p] = y[p] + q.k.offEy;
+    xb[p] = x[p] + q.k.offBx; yb[p] = y[p] + q.k.offBy;
+    if (ORDER == 2) {
+      xe[p] = xe[p] + 0.5; ye[p] = ye[p] + 0.5; xb[p] = xb[p] + 0.5; yb[p] = yb[p] + 0.5;
+    }
+    ixe[p] = (int)xe[p]; iye[p] = (int)ye[p]; ixb[p] = (int)xb[p]; iyb[p] = (int)yb[p];
+    ok = ok && ixe[p] == c.cix && iye[p] == c.ciy;
+  }
+  if (c.fast && __all_sync(SKB_FULL, ok)) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      double e[3], b[3];
+      if constexpr (ORDER == 1) {
+        const double dx = xe[p] - (double)ixe[p], tx = 1.0 - dx;
+        const double dy = ye[p] - (double)iye[p], ty = 1.0 - dy;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          e[k] = dy * (dx * c.eC[3][k] + tx * c.eC[2][k]) + ty * (dx * c.eC[1][k] + tx * c.eC[0][k]);
+        const double *bp = sB + ((iyb[p] - w.y0) * CS_WS + (ixb[p] - w.x0)) * 3;
+        const double dxb = xb[p] - (double)ixb[p], txb = 1.0 - dxb;
+        const double dyb = yb[p] - (double)iyb[p], tyb = 1.0 - dyb;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          b[k] = dyb * (dxb * bp[(CS_WS + 1) * 3 + k] + txb * bp[CS_WS * 3 + k]) +
+                 tyb * (dxb * bp[3 + k] + txb * bp[k]);
+      } else {
+        // tsc_weights, particle_push.pxd:37-57 (xe, xb already carry the + 0.5)
+        double wmx, w0x, wpx, wmy, w0y, wpy;
+        {
+          const double d = xe[p] - (double)ixe[p] - 0.5; w0x = 0.75 - d * d;
+          const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
+        }
+        {
+          const double d = ye[p] - (double)iye[p] - 0.5; w0y = 0.75 - d * d;
+          const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
+        }
+        const double *ep = sE + ((c.ciy - 1 - w.y0) * CS_WS + (c.cix - 1 - w.x0)) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          e[k] = wmy * (wmx * ep[k] + w0x * ep[3 + k] + wpx * ep[6 + k]) +
+                 w0y * (wmx * ep[CS_WS * 3 + k] + w0x * ep[CS_WS * 3 + 3 + k] +
+                        wpx * ep[CS_WS * 3 + 6 + k]) +
+                 wpy * (wmx * ep[2 * CS_WS * 3 + k] + w0x * ep[2 * CS_WS * 3 + 3 + k] +
+                        wpx * ep[2 * CS_WS * 3 + 6 + k]);
+        {
+          const double d = xb[p] - (double)ixb[p] - 0.5; w0x = 0.75 - d * d;
+          const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
+        }
+        {
+          const double d = yb[p] - (double)iyb[p] - 0.5; w0y = 0.75 - d * d;
+          const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
+        }
+        const double *bp = sB + ((iyb[p] - 1 - w.y0) * CS_WS + (ixb[p] - 1 - w.x0)) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          b[k] = wmy * (wmx * bp[k] + w0x * bp[3 + k] + wpx * bp[6 + k]) +
+                 w0y * (wmx * bp[CS_WS * 3 + k] + w0x * bp[CS_WS * 3 + 3 + k] +
+                        wpx * bp[CS_WS * 3 + 6 + k]) +
+                 wpy * (wmx * bp[2 * CS_WS * 3 + k] + w0x * bp[2 * CS_WS * 3 + 3 + k] +
+                        wpx * bp[2 * CS_WS * 3 + 6 + k]);
+      }
+      rescale_and_kick<MODIFIED>(e, b, g, q.k, y[p], vx[p], vy[p], vz[p]);
+    }
+  } else {
+#pragma unroll 1
+    for (int p = 0; p < NP; p++)
+      if (act[p])
+        fields_and_kick<ORDER, MODIFIED>(sE, sB, w, CS_WS, E, B, g, q.k, x[p], y[p], vx[p],
+                                         vy[p], vz[p]);
+  }
+  // ---- drift, boundary epilogue, new stencil-base cell --------------------------------
+  bool odd = false;                                   // x wrap needed or leaver: rare
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    x[p] = x[p] + vx[p] * q.dtdsx;                    // drift_particle, particle_push.pxd:88-91
+    y[p] = y[p] + vy[p] * q.dtdsy;
+    if (q.flags & SKB_EPI_SHEAR) {                    // particle_boundary.pyx:41-49
+      if (y[p] < 0.0) { x[p] = x[p] - q.x_boost; vx[p] = vx[p] - q.vx_boost; }
+      if (y[p] >= nyd) { x[p] = x[p] + q.x_boost; vx[p] = vx[p] + q.vx_boost; }
+    }
+    odd = odd || (act[p] && (!(x[p] >= 0.0 && x[p] < nxd) || y[p] < g.e0 || y[p] >= g.e1));
+  }
+  bool leaver[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) leaver[p] = false;
+  if (__any_sync(SKB_FULL, odd)) {
+#pragma unroll 1
+    for (int p = 0; p < NP; p++) {
+      if (!act[p]) continue;
+      if ((q.flags & SKB_EPI_PERIODIC_X) && !(x[p] >= 0.0 && x[p] < nxd)) x[p] = wrap_x(x[p], nxd);
+      if (y[p] < g.e0 || y[p] >= g.e1) {              // leaves the slab: cppmove2's pack
+        leaver[p] = true;
+        double *buf; int slot; double yy = y[p];
+        if (yy < g.e0) {
+          if (q.rank == 0) yy += nyd;
+          slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
+        } else {
+          if (q.rank == q.nvp - 1) yy -= nyd;
+          slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
+        }
+        if (slot < q.nbmax) {
+          double *r = buf + (size_t)slot * 5;
+          r[0] = x[p]; r[1] = yy; r[2] = vx[p]; r[3] = vy[p]; r[4] = vz[p];
+        } else {
+          atomicOr(q.counts + 3, 2);
+        }
+      }
+    }
+  }
+  // new stencil-base cell (== cell_key without the clamp: a particle outside the array is
+  // a mover and gets clamped by the insertion) and, for PD, the deposit weights
+  int nix[NP], niy[NP];
+  double wx[NP][NS], wy[NP][NS];
+  bool stay[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    double xs = x[p] + q.key.offx, ys = y[p] + q.key.offy;
+    if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+    particle_terms<ORDER>(xs, ys, nix[p], niy[p], wx[p], wy[p]);
+    stay[p] = act[p] && !leaver[p] && nix[p] == c.cix && niy[p] == c.ciy;
+  }
+  // ---- movers: staged in shared memory; stayers: compacted write-back ----------------
+  bool parked[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const bool mover = act[p] && !leaver[p] && !stay[p];
+    parked[p] = cs_stage_movers<PD>(mover, x[p], y[p], vx[p], vy[p], vz[p], mv, mbuf, s_nrows,
+                                    scr, scr_rows, q);
+    stay[p] = stay[p] || parked[p];
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    // compacted to the front of the cell's range: always behind the reads (everything up to
+    // the end of this block is already in the ring)
+    const unsigned sm = __ballot_sync(SKB_FULL, stay[p]);
+    if (stay[p]) {
+      double *px = P.x + ((long long)c.s + c.wcur + __popc(sm & lt));
+      px[0] = x[p]; px[pstride] = y[p]; px[2 * pstride] = vx[p]; px[3 * pstride] = vy[p];
+      px[4 * pstride] = vz[p];
+      if constexpr (PD != 0) {
+        const double vxr = vx[p] + dq.dp.S * (y[p] * g.dy + g.y0);     // deposit.pxd:24
+        if (!parked[p]) accumulate<ORDER>(c.acc, wx[p], wy[p], vxr, vy[p], vz[p]);
+        else stray_particle_emit<NS>(wx[p], wy[p], nix[p], niy[p], vxr, vy[p], vz[p], sS, w,
+                                     CS_WS, dq.cur, g);
+      }
+    }
+    c.wcur += __popc(sm);
+  }
+}
+
+// one warp reduction and one emit per cell (see deposit_cells_kernel)
+template <int NS>
+__device__ __forceinline__ void cs_emit_cell(Acc<NS> &acc, bool in_window, double *sS,
+                                             const Window &w, double *cur, const DevGrid &g) {
+  const int lane = threadIdx.x & 31;
+  if constexpr (NS == 2) {
+    warp_reduce_scatter<16>(acc.v, lane);
+    if (lane < 16)
+      emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sS, w, CS_WS,
+                   cur, g);
+  } else {
+    warp_reduce_scatter<32>(acc.v, lane);
+    warp_reduce_scatter<4>(acc.v + 32, lane);
+    emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sS, w, CS_WS, cur,
+                 g);
+    if (lane < 4)
+      emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sS, w,
+                   CS_WS, cur, g);
+  }
 }
 
 // ---- the kernel --------------------------------------------------------------------------
 // PD = 0: push;  PD = 3: push + full-step deposit into dq.cur (raw sums, not normalised)
+// tm64 / tm32: tensor maps of the [5][pstride] particle tensor with boxes of 5 x 64 and
+// 5 x 32 slots
 template <int ORDER, bool MODIFIED, int PD>
 __global__ void __launch_bounds__(CS_THREADS, (ORDER == 2 && PD != 0) ? 1 : CS_MINB)
-cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
+cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
+                   const __grid_constant__ CUtensorMap tm32, skb_particles_t P,
+                   long long pstride, const double *__restrict__ E,
                    const double *__restrict__ B, DevGrid g, GapPush q, GapDeposit dq) {
   constexpr int NS = ORDER + 1;
   constexpr int LO = (ORDER == 2) ? 1 : 0;
   extern __shared__ __align__(128) double smem[];
-  double *sE = smem;
+  double *rings = smem;                                       // [warps][CS_NST][5][CS_STAGE]
+  double *mbufs = rings + CS_WARPS * CS_NST * CS_STAGE_D;     // [warps][CS_MROWS][5]
+  double *sE = mbufs + CS_WARPS * CS_MROWS * 5;
   double *sB = sE + CS_WIN3;
   double *sS = sB + CS_WIN3;                                  // (PD) window of the sources
-  double *rings = sS + (PD ? CS_WIN4 : 0);                    // [warps][CS_NST][5][CS_STAGE]
-  double *mbufs = rings + CS_WARPS * CS_NST * CS_STAGE_D;     // [warps][CS_MROWS][5]
-  unsigned long long *bars = (unsigned long long *)(mbufs + CS_WARPS * CS_MROWS * 5);
+  unsigned long long *bars = (unsigned long long *)(sS + (PD ? CS_WIN4 : 0));
   __shared__ int s_blk, s_nrows;
   __shared__ int s_nstay[CS_CELLS];
 
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
   const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
   const int c0 = (tile << 8) + (half << 7);
   const int wc0 = c0 + wv * CS_CPW;
@@ -285,18 +580,13 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
   stage_window(sB, B, w, CS_WS, g);
   __syncthreads();
   double *const scr = s_blk >= 0 ? q.scratch + (size_t)s_blk * q.scratch_rows * 5 : nullptr;
-  const int scr_rows = s_blk >= 0 ? q.scratch_rows : 0;
-  const double nxd = (double)g.nx, nyd = (double)g.ny;
-  const int ciy = by + wv;
-  // lanes 0..4 feed the ring: lane k copies array k
-  const double *const my_arr = lane == 0 ? P.x : lane == 1 ? P.y : lane == 2 ? P.vx
-                               : lane == 3 ? P.vy : P.vz;
+  const int scr_rows = s_blk >= 0 ? (q.scratch_rows & ~31) : 0;    // whole halves only
   double *const ring = rings + (size_t)wv * (CS_NST * CS_STAGE_D);
   const unsigned ring_s = cs_smem(ring);
   double *const mbuf = mbufs + (size_t)wv * (CS_MROWS * 5);
-  int mcount = 0;                                  // mover rows staged so far by this warp
-  double *cur_dst = nullptr;                       // where the half being filled will go
-  bool parking = false;                            // mover lists full: movers stay put
+  CsMovers mv;
+  mv.count = 0;
+  mv.slot = cs_reserve<PD>(&s_nrows, scr_rows, q.counts, q.movers, q.mover_cap);
 
 #define CS_CNT(j) __shfl_sync(SKB_FULL, my_cnt, (j))
 #define CS_ADVANCE(j, base)                                    \
@@ -307,16 +597,19 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
       while (j < CS_CPW && CS_CNT(j) == 0) j++;                \
     }                                                          \
   } while (0)
-  // one stage = up to 64 particles of ONE cell: 5 bulk copies of `bytes` each
+  // one stage = up to 64 particles of ONE cell: a [5 x 64] box, or [5 x 32] when no more
+  // than 32 particles are left (the box may reach into the cell's free slots or beyond:
+  // those columns are never looked at)
 #define CS_FETCH(stage, j, base)                                                        \
   do {                                                                                  \
-    const int fs_ = __shfl_sync(SKB_FULL, my_start, (j));                               \
-    const int np_ = (min(CS_STAGE, CS_CNT(j) - (base)) + 1) & ~1;                       \
-    const unsigned bar_ = bar0 + 8 * (stage);                                           \
-    if (lane == 0) cs_mbar_expect_tx(bar_, 5u * 8u * (unsigned)np_);                    \
-    if (lane < 5)                                                                       \
-      cs_bulk_load(ring_s + (unsigned)(((stage) * 5 + lane) * CS_STAGE) * 8u,           \
-                   my_arr + ((size_t)fs_ + (base)), 8u * (unsigned)np_, bar_);          \
+    const int fs_ = __shfl_sync(SKB_FULL, my_start, (j)) + (base);                      \
+    const bool big_ = CS_CNT(j) - (base) > 32;                                          \
+    if (lane == 0) {                                                                    \
+      const unsigned bar_ = bar0 + 8 * (stage);                                         \
+      cs_mbar_expect_tx(bar_, big_ ? 5u * 8u * 64u : 5u * 8u * 32u);                    \
+      cs_tma_load_2d(ring_s + (unsigned)((stage) * CS_STAGE_D) * 8u, big_ ? &tm64 : &tm32, \
+                     fs_, 0, bar_);                                                     \
+    }                                                                                   \
   } while (0)
 
   int fj = 0, fbase = 0;
@@ -325,233 +618,51 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
 #pragma unroll
   for (int st = 0; st < CS_NST; st++)
     if (fj < CS_CPW) { CS_FETCH(st, fj, fbase); CS_ADVANCE(fj, fbase); }
-  int stage = 0, wcur = 0;                         // wcur: stayers written so far
+  int stage = 0, n = 0;
   unsigned phases = 0;                             // parity bit of every ring stage
-  Acc<NS> acc;                                     // (PD) stencil sums of the current cell
-  double eC[4][3];                                 // (CIC) E stencil of the current cell
-  bool cell_fast = false;
-  int cix = 0, s = 0, n = 0;
+  CsCell<ORDER, PD> c;
+  c.ciy = by + wv; c.cix = 0; c.s = 0; c.wcur = 0; c.fast = false;
+  c.ysafe = (double)c.ciy + 0.25 - q.k.offEy - (ORDER == 2 ? 0.5 : 0.0);
+  c.xsafe = 0.0;
   while (cj < CS_CPW) {
     if (cbase == 0) {                              // first stage of a cell
-      cix = bx + cj;
-      s = __shfl_sync(SKB_FULL, my_start, cj);
+      c.cix = bx + cj;
+      c.s = __shfl_sync(SKB_FULL, my_start, cj);
       n = CS_CNT(cj);
+      c.xsafe = (double)c.cix + 0.25 - q.k.offEx - (ORDER == 2 ? 0.5 : 0.0);
       // every stencil a particle filed under this cell can touch lies inside the window
-      cell_fast = cix - LO >= w.x0 && cix + 2 < w.x1 && ciy - LO >= w.y0 && ciy + 2 < w.y1;
-      if (ORDER == 1 && cell_fast) {
-        const double *eb = sE + ((ciy - w.y0) * CS_WS + (cix - w.x0)) * 3;
+      c.fast = c.cix - LO >= w.x0 && c.cix + 2 < w.x1 && c.ciy - LO >= w.y0 && c.ciy + 2 < w.y1;
+      if (ORDER == 1 && c.fast) {
+        const double *eb = sE + ((c.ciy - w.y0) * CS_WS + (c.cix - w.x0)) * 3;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          eC[0][k] = eb[k]; eC[1][k] = eb[3 + k];
-          eC[2][k] = eb[CS_WS * 3 + k]; eC[3][k] = eb[CS_WS * 3 + 3 + k];
+          c.eC[0][k] = eb[k]; c.eC[1][k] = eb[3 + k];
+          c.eC[2][k] = eb[CS_WS * 3 + k]; c.eC[3][k] = eb[CS_WS * 3 + 3 + k];
         }
       }
       if constexpr (PD != 0) {
 #pragma unroll
-        for (int i = 0; i < NS * NS * 4; i++) acc.v[i] = 0.0;
-        acc.ix = cix; acc.iy = ciy;
+        for (int i = 0; i < NS * NS * 4; i++) c.acc.v[i] = 0.0;
+        c.acc.ix = c.cix; c.acc.iy = c.ciy;
       }
     }
     while (!cs_mbar_try_wait(bar0 + 8 * stage, (phases >> stage) & 1u)) {}
     phases ^= 1u << stage;
-    const double *pb = ring + stage * CS_STAGE_D;
+    const double *pp = ring + stage * CS_STAGE_D + lane;
     const int nrem = n - cbase;
-#pragma unroll 1
-    for (int u = 0; u < CS_STAGE / 32; u++) {
-      if (u * 32 >= nrem) break;
-      const bool act = u * 32 + lane < nrem;
-      bool stay = false, mover = false, parked = false;
-      int nix = 0, niy = 0;
-      double x = 0, y = 0, vx = 0, vy = 0, vz = 0;
-      double wx[NS], wy[NS];
-#pragma unroll
-      for (int i = 0; i < NS; i++) wx[i] = wy[i] = 0.0;
-      if (act) {
-        const double *pp = pb + u * 32 + lane;
-        x = pp[0]; y = pp[CS_STAGE]; vx = pp[2 * CS_STAGE]; vy = pp[3 * CS_STAGE];
-        vz = pp[4 * CS_STAGE];
-      }
-      // field gather: shared stencil of the cell (E) / per-lane window reads (B); a lane
-      // whose indices are not the ones its cell promises sends the warp down the generic
-      // path for this block
-      double xe = x + q.k.offEx, ye = y + q.k.offEy, xb = x + q.k.offBx, yb = y + q.k.offBy;
-      if (ORDER == 2) { xe = xe + 0.5; ye = ye + 0.5; xb = xb + 0.5; yb = yb + 0.5; }
-      const int ixe = (int)xe, iye = (int)ye, ixb = (int)xb, iyb = (int)yb;
-      const bool ok = !act || (ixe == cix && iye == ciy && (unsigned)(ixb - cix) <= 1u &&
-                               (unsigned)(iyb - ciy) <= 1u);
-      if (cell_fast && __all_sync(SKB_FULL, ok)) {
-        if (act) {
-          double e[3], b[3];
-          if constexpr (ORDER == 1) {
-            const double dx = xe - (double)ixe, tx = 1.0 - dx;
-            const double dy = ye - (double)iye, ty = 1.0 - dy;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-              e[k] = dy * (dx * eC[3][k] + tx * eC[2][k]) + ty * (dx * eC[1][k] + tx * eC[0][k]);
-            const double *bp = sB + ((iyb - w.y0) * CS_WS + (ixb - w.x0)) * 3;
-            const double dxb = xb - (double)ixb, txb = 1.0 - dxb;
-            const double dyb = yb - (double)iyb, tyb = 1.0 - dyb;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-              b[k] = dyb * (dxb * bp[(CS_WS + 1) * 3 + k] + txb * bp[CS_WS * 3 + k]) +
-                     tyb * (dxb * bp[3 + k] + txb * bp[k]);
-          } else {
-            // tsc_weights, particle_push.pxd:37-57 (xe, xb already carry the + 0.5)
-            double wmx, w0x, wpx, wmy, w0y, wpy;
-            {
-              const double d = xe - (double)ixe - 0.5; w0x = 0.75 - d * d;
-              const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
-            }
-            {
-              const double d = ye - (double)iye - 0.5; w0y = 0.75 - d * d;
-              const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
-            }
-            const double *ep = sE + ((ciy - 1 - w.y0) * CS_WS + (cix - 1 - w.x0)) * 3;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-              e[k] = wmy * (wmx * ep[k] + w0x * ep[3 + k] + wpx * ep[6 + k]) +
-                     w0y * (wmx * ep[CS_WS * 3 + k] + w0x * ep[CS_WS * 3 + 3 + k] +
-                            wpx * ep[CS_WS * 3 + 6 + k]) +
-                     wpy * (wmx * ep[2 * CS_WS * 3 + k] + w0x * ep[2 * CS_WS * 3 + 3 + k] +
-                            wpx * ep[2 * CS_WS * 3 + 6 + k]);
-            {
-              const double d = xb - (double)ixb - 0.5; w0x = 0.75 - d * d;
-              const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
-            }
-            {
-              const double d = yb - (double)iyb - 0.5; w0y = 0.75 - d * d;
-              const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
-            }
-            const double *bp = sB + ((iyb - 1 - w.y0) * CS_WS + (ixb - 1 - w.x0)) * 3;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-              b[k] = wmy * (wmx * bp[k] + w0x * bp[3 + k] + wpx * bp[6 + k]) +
-                     w0y * (wmx * bp[CS_WS * 3 + k] + w0x * bp[CS_WS * 3 + 3 + k] +
-                            wpx * bp[CS_WS * 3 + 6 + k]) +
-                     wpy * (wmx * bp[2 * CS_WS * 3 + k] + w0x * bp[2 * CS_WS * 3 + 3 + k] +
-                            wpx * bp[2 * CS_WS * 3 + 6 + k]);
-          }
-          rescale_and_kick<MODIFIED>(e, b, g, q.k, y, vx, vy, vz);
-        }
-      } else if (act) {
-        fields_and_kick<ORDER, MODIFIED>(sE, sB, w, CS_WS, E, B, g, q.k, x, y, vx, vy, vz);
-      }
-      bool leaver = false;
-      if (act) {
-        x = x + vx * q.dtdsx;                      // drift_particle, particle_push.pxd:88-91
-        y = y + vy * q.dtdsy;
-        if (q.flags & SKB_EPI_SHEAR) {             // particle_boundary.pyx:41-49
-          if (y < 0.0) { x = x - q.x_boost; vx = vx - q.vx_boost; }
-          if (y >= nyd) { x = x + q.x_boost; vx = vx + q.vx_boost; }
-        }
-        if ((q.flags & SKB_EPI_PERIODIC_X) && !(x >= 0.0 && x < nxd)) x = wrap_x(x, nxd);
-        leaver = y < g.e0 || y >= g.e1;
-        // new stencil-base cell (== cell_key without the clamp: a particle outside the
-        // array is a mover and gets clamped by the insertion) and, for PD, the weights
-        double xs = x + q.key.offx, ys = y + q.key.offy;
-        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
-        particle_terms<ORDER>(xs, ys, nix, niy, wx, wy);
-        stay = !leaver && nix == cix && niy == ciy;
-        mover = !leaver && !stay;
-      }
-      if (__any_sync(SKB_FULL, leaver)) {
-        if (leaver) {                              // leaves the slab: cppmove2's pack
-          double *buf; int slot; double yy = y;
-          if (yy < g.e0) {
-            if (q.rank == 0) yy += nyd;
-            slot = atomicAdd(q.counts + 1, 1); buf = q.sbufl;
-          } else {
-            if (q.rank == q.nvp - 1) yy -= nyd;
-            slot = atomicAdd(q.counts + 2, 1); buf = q.sbufr;
-          }
-          if (slot < q.nbmax) {
-            double *r = buf + (size_t)slot * 5;
-            r[0] = x; r[1] = yy; r[2] = vx; r[3] = vy; r[4] = vz;
-          } else {
-            atomicOr(q.counts + 3, 2);
-          }
-        }
-      }
-      // movers: AoS rows in the warp's shared buffer; a half (32 rows, 1280 B) goes out
-      // with one TMA bulk store to a destination reserved BEFORE its first row is staged
-      const unsigned mm = __ballot_sync(SKB_FULL, mover);
-      if (mm) {
-        if (!parking && cur_dst == nullptr) {
-          cur_dst = cs_reserve<PD>(&s_nrows, scr, scr_rows & ~31, q);
-          parking = cur_dst == nullptr;
-        }
-        if (parking) {
-          parked = mover; stay = stay || mover; mover = false;
-        } else {
-          const int after = mcount + __popc(mm);
-          const int boundary = (mcount | 31) + 1;
-          const bool cross = after >= boundary;
-          double *nxt = nullptr;
-          if (cross) {          // the half about to be (re)entered must have been read out
-            if (lane == 0) cs_bulk_wait_read();
-            __syncwarp();
-            if (after > boundary) {
-              nxt = cs_reserve<PD>(&s_nrows, scr, scr_rows & ~31, q);
-              parking = nxt == nullptr;
-            }
-          }
-          if (mover) {
-            const int pos = mcount + __popc(mm & lt);
-            if (parking && pos >= boundary) {
-              parked = true; stay = true; mover = false;
-            } else {
-              double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
-              r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
-            }
-          }
-          if (cross) {
-            const int h = (mcount >> 5) & 1;       // the half that is complete now
-            cs_fence_async_smem();
-            __syncwarp();
-            if (lane == 0) cs_bulk_store(cur_dst, cs_smem(mbuf + h * 160), 1280u);
-            cur_dst = nxt;
-          }
-          mcount = (cross && parking) ? boundary : after;
-        }
-      }
-      // stayers: compacted to the front of the cell's range (always behind the reads:
-      // wcur <= cbase + u*32, and everything up to cbase + 64 is already in the ring)
-      const unsigned sm = __ballot_sync(SKB_FULL, stay);
-      if (stay) {
-        const long long d = (long long)s + wcur + __popc(sm & lt);
-        P.x[d] = x; P.y[d] = y; P.vx[d] = vx; P.vy[d] = vy; P.vz[d] = vz;
-        if constexpr (PD != 0) {
-          const double vxr = vx + dq.dp.S * (y * g.dy + g.y0);     // deposit.pxd:24
-          if (!parked) accumulate<ORDER>(acc, wx, wy, vxr, vy, vz);
-          else stray_particle_emit<NS>(wx, wy, nix, niy, vxr, vy, vz, sS, w, CS_WS, dq.cur, g);
-        }
-      }
-      wcur += __popc(sm);
-    }
+    if (nrem > 32)
+      cs_block<ORDER, MODIFIED, PD, 2>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
+                                       dq, mbuf, &s_nrows, scr, scr_rows);
+    else
+      cs_block<ORDER, MODIFIED, PD, 1>(pp, 32, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
+                                       dq, mbuf, &s_nrows, scr, scr_rows);
     __syncwarp();                                  // stage fully read: refill it
     int nj = cj, nbase = cbase;
     CS_ADVANCE(nj, nbase);
     if (nj != cj) {                                // the cell is finished
-      if (lane == 0) { q.gap_count[wc0 + cj] = wcur; s_nstay[wv * CS_CPW + cj] = wcur; }
-      wcur = 0;
-      if constexpr (PD != 0) {
-        // one warp reduction and one emit per cell (see deposit_cells_kernel)
-        const bool in_window = cell_fast;
-        if constexpr (NS == 2) {
-          warp_reduce_scatter<16>(acc.v, lane);
-          if (lane < 16)
-            emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sS, w,
-                         CS_WS, dq.cur, g);
-        } else {
-          warp_reduce_scatter<32>(acc.v, lane);
-          warp_reduce_scatter<4>(acc.v + 32, lane);
-          emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sS, w,
-                       CS_WS, dq.cur, g);
-          if (lane < 4)
-            emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sS,
-                         w, CS_WS, dq.cur, g);
-        }
-      }
+      if (lane == 0) { q.gap_count[wc0 + cj] = c.wcur; s_nstay[wv * CS_CPW + cj] = c.wcur; }
+      c.wcur = 0;
+      if constexpr (PD != 0) cs_emit_cell<NS>(c.acc, c.fast, sS, w, dq.cur, g);
     }
     cj = nj; cbase = nbase;
     if (fj < CS_CPW) { CS_FETCH(stage, fj, fbase); CS_ADVANCE(fj, fbase); }
@@ -560,21 +671,24 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
 #undef CS_CNT
 #undef CS_ADVANCE
 #undef CS_FETCH
-  // the rows still in the warp's buffer: the unused part of the half becomes padding
-  {
-    const int rem = mcount & 31;
-    if (rem && cur_dst != nullptr) {
-      const int h = (mcount >> 5) & 1;
-      if (lane >= rem) mbuf[(h * 32 + lane) * 5] = __longlong_as_double(GAP_PAD_BITS);
-      cs_fence_async_smem();
-      __syncwarp();
-      if (lane == 0) cs_bulk_store(cur_dst, cs_smem(mbuf + h * 160), 1280u);
+  // the rows still in the warp's buffer: the unused part of the half becomes padding (a
+  // reservation is always written in full)
+  if (mv.slot != CS_NOSLOT) {
+    const int rem = mv.count & 31;
+    const int h = (mv.count >> 5) & 1;
+    if (lane >= rem) mbuf[(h * 32 + lane) * 5] = __longlong_as_double(GAP_PAD_BITS);
+    cs_fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      double *dst = (mv.slot & CS_GLOBAL) ? q.movers + (size_t)(mv.slot & ~CS_GLOBAL) * 5
+                                          : scr + (size_t)mv.slot * 5;
+      cs_bulk_store(dst, cs_smem(mbuf + h * 160), 1280u);
     }
-    if (lane == 0) cs_bulk_wait_all();             // my scratch rows are in memory
   }
+  if (lane == 0) cs_bulk_wait_all();               // my scratch rows are in memory
   // phase B: all cells of this CTA are compacted; place the parked rows
   __syncthreads();
-  const int nrows = min(s_nrows, scr_rows & ~31);  // (reservations are whole halves)
+  const int nrows = min(s_nrows, scr_rows);        // (reservations are whole halves)
   if (nrows > 0) {
     if (threadIdx.x == 0) atomicAdd(q.counts + 4, nrows);            // statistics
     for (int r0 = 0; r0 < nrows; r0 += CS_THREADS * GAP_INS_ITEMS)
@@ -592,9 +706,10 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
       if (n1 <= n0) continue;
       const int st = __shfl_sync(SKB_FULL, my_start, j);
       const int ax = bx + j;
+      Acc<NS> &acc = c.acc;
 #pragma unroll
       for (int i = 0; i < NS * NS * 4; i++) acc.v[i] = 0.0;
-      acc.ix = ax; acc.iy = ciy;
+      acc.ix = ax; acc.iy = c.ciy;
       for (int i = n0 + lane; i < n1; i += 32) {
         const long long d = (long long)st + i;
         const double x = __ldcg(P.x + d), y = __ldcg(P.y + d), vx = __ldcg(P.vx + d),
@@ -608,22 +723,9 @@ cell_stream_kernel(skb_particles_t P, const double *__restrict__ E,
         if (ix == acc.ix && iy == acc.iy) accumulate<ORDER>(acc, wx, wy, vxr, vy, vz);
         else stray_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, sS, w, CS_WS, dq.cur, g);
       }
-      const bool in_window = ax - LO >= w.x0 && ax + 2 < w.x1 && ciy - LO >= w.y0 &&
-                             ciy + 2 < w.y1;
-      if constexpr (NS == 2) {
-        warp_reduce_scatter<16>(acc.v, lane);
-        if (lane < 16)
-          emit_one<NS>(acc.v[0], scatter_index<16>(lane), in_window, acc.ix, acc.iy, sS, w,
-                       CS_WS, dq.cur, g);
-      } else {
-        warp_reduce_scatter<32>(acc.v, lane);
-        warp_reduce_scatter<4>(acc.v + 32, lane);
-        emit_one<NS>(acc.v[0], scatter_index<32>(lane), in_window, acc.ix, acc.iy, sS, w,
-                     CS_WS, dq.cur, g);
-        if (lane < 4)
-          emit_one<NS>(acc.v[32], 32 + scatter_index<4>(lane), in_window, acc.ix, acc.iy, sS,
-                       w, CS_WS, dq.cur, g);
-      }
+      const bool in_window = ax - LO >= w.x0 && ax + 2 < w.x1 && c.ciy - LO >= w.y0 &&
+                             c.ciy + 2 < w.y1;
+      cs_emit_cell<NS>(acc, in_window, sS, w, dq.cur, g);
     }
     __syncthreads();
     flush_window(sS, w, CS_WS, dq.cur, g);
@@ -637,16 +739,52 @@ size_t cell_stream_smem(int pd) {
          CS_WARPS * CS_NST * sizeof(unsigned long long);
 }
 
+typedef CUresult (*cs_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                 const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map of the [5][stride] float64 particle tensor at `base` with a [5 x box] box
+static int cs_particle_map(CUtensorMap *tm, void *base, long long stride, int box) {
+  static cs_encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return (int)e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+    encode = (cs_encode_fn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)stride, 5};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(double)};
+  const cuuint32_t boxd[2] = {(cuuint32_t)box, 5};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, boxd, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 // pd: 0 = push, 3 = push + full-step deposit.  Returns cudaErrorNotSupported when the
 // configuration is not the one this kernel is built for (the caller then uses the
-// generic kernel of gapped.cu).
+// generic kernel of gapped.cu): tiles other than 16 x 16, or particle arrays that are not
+// the rows of one [5][stride] tensor (the TMA descriptor needs a constant row pitch).
 int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const double *E,
                        const double *B, const DevGrid &g, const GapPush &q,
                        const GapDeposit &dq, int ntiles, cudaStream_t st) {
   if (q.key.tlx != 4 || q.key.tly != 4) return (int)cudaErrorNotSupported;
   if (pd != 0 && pd != 3) return (int)cudaErrorNotSupported;
-  if (q.scratch_rows & 1) return (int)cudaErrorInvalidValue;     // 16-byte rows for TMA
-  void (*k)(skb_particles_t, const double *, const double *, DevGrid, GapPush, GapDeposit);
+  const long long stride = p.y - p.x;
+  if (stride <= 0 || (stride & 1) || p.vx - p.y != stride || p.vy - p.vx != stride ||
+      p.vz - p.vy != stride || ((uintptr_t)p.x & 15))
+    return (int)cudaErrorNotSupported;
+  CUtensorMap tm64, tm32;
+  int rc = cs_particle_map(&tm64, (void *)p.x, stride, 64);
+  if (rc) return rc;
+  rc = cs_particle_map(&tm32, (void *)p.x, stride, 32);
+  if (rc) return rc;
+  void (*k)(const CUtensorMap, const CUtensorMap, skb_particles_t, long long, const double *,
+            const double *, DevGrid, GapPush, GapDeposit);
   if (pd == 0) {
     if (order == 1) k = modified ? cell_stream_kernel<1, true, 0> : cell_stream_kernel<1, false, 0>;
     else k = modified ? cell_stream_kernel<2, true, 0> : cell_stream_kernel<2, false, 0>;
@@ -672,7 +810,7 @@ int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const
     }
     if (q.npool < resident[slot]) return (int)cudaErrorInvalidValue;
   }
-  k<<<ntiles * 2, CS_THREADS, smem, st>>>(p, E, B, g, q, dq);
+  k<<<ntiles * 2, CS_THREADS, smem, st>>>(tm64, tm32, p, stride, E, B, g, q, dq);
   SKB_CHECK_LAUNCH();
   return 0;
 }

@@ -43,9 +43,9 @@ def main():
             super().__init__(manifold, 4*int(Nmax), **kw)
             self.gapped = True
 
-        def _gap_finish(self, cnt, *args):
+        def _gap_finish(self, cnt, *args, **kw):
             pushes[0] += 1
-            return super()._gap_finish(cnt, *args)
+            return super()._gap_finish(cnt, *args, **kw)
 
     ns = types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,

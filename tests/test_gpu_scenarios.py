@@ -33,9 +33,9 @@ def namespace(gapped=False):
             super().__init__(manifold, 4*int(Nmax), **kw)
             self.gapped = True
 
-        def _gap_finish(self, cnt, *args):
+        def _gap_finish(self, cnt, *args, **kw):
             GAPPED_PUSHES[0] += 1
-            return super()._gap_finish(cnt, *args)
+            return super()._gap_finish(cnt, *args, **kw)
 
     return types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,

@@ -7,14 +7,16 @@
 // organised around what ncu showed about that kernel (514 warp instructions per 32
 // particles, two thirds of the issue slots busy, 145 of them fp64 arithmetic):
 //
-//  * one warp streams the particles of one ROW of 16 cells of a 16 x 16 tile; a CTA of 8
-//    warps owns half a tile and stages its own (8+5) x (16+5) window of E and B;
+//  * one warp streams the particles of one ROW of 16 cells of a 16 x 16 tile; a CTA of 4
+//    warps owns a quarter of a tile and stages its own (4+5) x (16+5) window of E and B
+//    (small CTAs: four are resident per SM, so the block-wide barrier in front of the
+//    re-insertion phase of one of them is covered by the streams of the other three);
 //  * particles arrive through a per-warp ring of 64-particle stages, each filled by ONE
 //    TMA tensor copy (cp.async.bulk.tensor.2d + mbarrier complete_tx) of a [5 rows x 64
 //    slots] box of the [5][Nmax] particle tensor - one elected lane issues it, nobody
-//    computes per-lane load addresses; a stage is processed as two particles per lane, so
-//    every lane carries two independent dependency chains (4 warps per scheduler are too
-//    few to hide the fp64 / shared-memory latencies otherwise);
+//    computes per-lane load addresses; (an optional mode processes a stage as two particles
+//    per lane; with 128 registers per thread the compiler cannot interleave the two
+//    chains and it is slower, see CS_NP2);
 //  * all particles of a cell share the E stencil (the sort key IS the E-gather / deposit
 //    base cell), so for CIC the 2 x 2 x 3 E values live in registers for the whole cell;
 //    B is read per lane from the shared window (its base cell differs by the half-cell
@@ -36,22 +38,44 @@
 #include <cuda.h>
 #include "gapped.cuh"
 
-#define CS_THREADS 256
-#define CS_WARPS 8
+#ifndef CS_WARPS
+#define CS_WARPS 4           // warps per CTA (8: half a tile, 4: a quarter)
+#endif
+#define CS_THREADS (32 * CS_WARPS)
+#define CS_PARTS (16 / CS_WARPS)    // CTAs per tile
 #define CS_CPW 16            // cells per warp: one row of the 16 x 16 tile
-#define CS_CELLS 128         // cells per CTA: half a tile
-#define CS_STAGE 64          // particles per ring stage
+#define CS_CELLS (16 * CS_WARPS)    // cells per CTA
+#ifndef CS_STAGE
+#define CS_STAGE 64          // particles per ring stage (64 or 32)
+#endif
+#ifndef CS_NP2
+#define CS_NP2 0              // 1: blocks of 64 particles run as two particles per lane (measured: no gain)
+#endif
+#ifndef CS_ABLATE
+#define CS_ABLATE 0          // timing experiments only (results are wrong): 1 drop movers,
+#endif                       // 2 no stayer stores, 4 no gather + kick, 8 no phase B
+#ifndef CS_L2HINTS
+#define CS_L2HINTS 0         // particle stream: L2 evict_first; parked rows: evict_last
+#endif
+#ifndef CS_HOIST_E
+#define CS_HOIST_E 1         // (CIC) the cell's E stencil lives in registers
+#endif
+// Measured on config 5 (one launch, 1.07e9 particles; tools/build_variants.py +
+// tools/run_ablate.sh, gpurun_out r2d-r2j): 4 warps x 4 CTAs/SM x 2 stages 22.0 ms;
+// 8 warps x 2 CTAs x 3 stages 23.3; 4 x 4 x 3 stages 24.8; 3 CTAs of 8 warps at 80
+// registers (32-particle stages) 24.0; 5 CTAs of 4 warps at 102 registers 27.3 (spills);
+// two particles per lane 25.3; L2 evict_first / evict_last hints 23.2.
 #ifndef CS_NST
-#define CS_NST 3             // ring stages per warp
+#define CS_NST 2             // ring stages per warp
 #endif
 #ifndef CS_MINB
-#define CS_MINB 2            // resident CTAs per SM aimed at
+#define CS_MINB 4            // resident CTAs per SM aimed at
 #endif
 #define CS_MROWS 64          // mover rows buffered per warp: two halves of 32
 #define CS_WS 21             // window stride in cells: 16 + SKB_HALO_LO + SKB_HALO_HI
-#define CS_WR 13             // window rows of a half tile: 8 + SKB_HALO_LO + SKB_HALO_HI
-#define CS_WIN3 832          // doubles reserved per Float3 window (13*21*3 = 819, 128 B multiple)
-#define CS_WIN4 1104         // doubles reserved for the Float4 window (13*21*4 = 1092)
+#define CS_WR (CS_WARPS + 5)  // window rows: the CTA's rows + SKB_HALO_LO + SKB_HALO_HI
+#define CS_WIN3 ((CS_WR * CS_WS * 3 + 15) & ~15)   // doubles reserved per Float3 window
+#define CS_WIN4 ((CS_WR * CS_WS * 4 + 15) & ~15)   // doubles reserved for the Float4 window
 #define CS_STAGE_D (5 * CS_STAGE)   // doubles per ring stage
 
 // ---- PTX wrappers: mbarrier + TMA bulk copies ----------------------------------------
@@ -78,20 +102,55 @@ __device__ __forceinline__ bool cs_mbar_try_wait(unsigned bar, unsigned parity) 
       : "memory");
   return ok != 0;
 }
+// L2 eviction policies: the particle stream is touched once per step (evict_first) while
+// the parked mover rows are read back by the same CTA ~100 us later (evict_last)
+__device__ __forceinline__ unsigned long long cs_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long cs_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // box of a 2-D tensor (global) -> shared, completion signalled on the mbarrier; c0 = slot
 // (inner coordinate), c1 = row
 __device__ __forceinline__ void cs_tma_load_2d(unsigned dst, const CUtensorMap *tm, int c0,
                                                int c1, unsigned bar) {
+#if CS_L2HINTS
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0),
+      "r"(c1), "l"(cs_policy_evict_first())
+      : "memory");
+#else
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+#endif
+}
+__device__ __forceinline__ void cs_store_stream(double *p, double v) {
+#if CS_L2HINTS
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v),
+               "l"(cs_policy_evict_first())
+               : "memory");
+#else
+  *p = v;
+#endif
 }
 // shared -> global, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void cs_bulk_store(void *dst, unsigned src, unsigned bytes) {
+#if CS_L2HINTS
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(dst), "r"(src), "r"(bytes), "l"(cs_policy_evict_last())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                "r"(src), "r"(bytes)
                : "memory");
+#endif
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void cs_bulk_wait_read() {      // sources may be overwritten
@@ -115,7 +174,9 @@ template <int ORDER, int PD>
 __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, int n, int i0,
                                               skb_particles_t P, const GapPush &q,
                                               const GapDeposit &dq, const DevGrid &g,
-                                              const Window &w, double *sS, int c0) {
+                                              const Window &w, double *sS, int c0,
+                                              int &mbase, int &mused, const int *s_gs,
+                                              int *s_cnt) {
   constexpr int NS = ORDER + 1;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -146,10 +207,13 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
     leader[t] = __ffs(peers) - 1; rank[t] = __popc(peers & lt);
     s[t] = cap[t] = base[t] = 0;
     if (local[t] && lane == leader[t]) {
-      base[t] = atomicAdd(q.gap_count + key[t], cnt);
-      s[t] = q.gap_start[key[t]]; cap[t] = q.gap_start[key[t] + 1] - s[t];
+      // slot ranges and live counts of the CTA's cells are in shared memory: no trip to
+      // L2 / HBM on this path
+      const int lc = key[t] - c0;
+      base[t] = atomicAdd(s_cnt + lc, cnt);
+      s[t] = s_gs[lc]; cap[t] = s_gs[lc + 1] - s[t];
       const int over = min(max(base[t] + cnt - cap[t], 0), cnt);
-      if (over) atomicSub(q.gap_count + key[t], over);  // cell full: those go to the leftovers
+      if (over) atomicSub(s_cnt + lc, over);      // cell full: those go to the leftovers
     }
   }
 #pragma unroll
@@ -174,15 +238,21 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
         }
       }
     }
-    // rows for other CTAs' cells: global mover list, one reservation per warp
+    // rows for other CTAs' cells: global mover list; slots are reserved GAP_MCHUNK at a
+    // time per warp (the list head is ONE address for the whole grid: an atomic per
+    // ballot would serialise in L2)
     const bool fwd = valid[t] && !local[t];
     const unsigned fm = __ballot_sync(SKB_FULL, fwd);
     if (fm) {
-      int fb = 0;
-      if (lane == __ffs(fm) - 1) fb = atomicAdd(q.counts + 0, __popc(fm));
-      fb = __shfl_sync(SKB_FULL, fb, __ffs(fm) - 1);
+      const int k = __popc(fm), room = GAP_MCHUNK - mused;
+      int nb = mbase;
+      if (k > room) {
+        if (lane == 0) nb = atomicAdd(q.counts + 0, GAP_MCHUNK);
+        nb = __shfl_sync(SKB_FULL, nb, 0);
+      }
       if (fwd) {
-        const int ms = fb + __popc(fm & lt);
+        const int r = __popc(fm & lt);
+        const int ms = r < room ? mbase + mused + r : nb + (r - room);
         if (ms < q.mover_cap) {
           double *o = q.movers + (size_t)ms * 5;
           o[0] = r0[t]; o[1] = r1[t]; o[2] = r2[t]; o[3] = r3[t]; o[4] = r4[t];
@@ -190,19 +260,29 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
           // list full: park the row in whichever of this CTA's cells has a free slot
           // (flag 1: some particles sit in a wrong cell, the layout gets rebuilt)
           for (int a = 0; a < CS_CELLS && !placed; a++) {
-            const int c = c0 + (((unsigned)key[t] + (unsigned)a) & (CS_CELLS - 1));
-            const int cs = q.gap_start[c], cc2 = q.gap_start[c + 1] - cs;
-            const int pos = atomicAdd(q.gap_count + c, 1);
+            const int c = ((unsigned)key[t] + (unsigned)a) & (CS_CELLS - 1);
+            const int cs = s_gs[c], cc2 = s_gs[c + 1] - cs;
+            const int pos = atomicAdd(s_cnt + c, 1);
             if (pos < cc2) {
               const long long d = (long long)cs + pos;
               P.x[d] = r0[t]; P.y[d] = r1[t]; P.vx[d] = r2[t]; P.vy[d] = r3[t]; P.vz[d] = r4[t];
               placed = true;
             } else {
-              atomicSub(q.gap_count + c, 1);
+              atomicSub(s_cnt + c, 1);
             }
           }
           atomicOr(q.counts + 3, placed ? 1 : 8);   // 8: no room anywhere, particle lost
         }
+      }
+      if (k > room) {
+        // the unused tail of the old chunk stays what it was made when it was reserved:
+        // padding (see below)
+        mbase = nb; mused = k - room;
+        for (int r = mused + lane; r < GAP_MCHUNK; r += 32)
+          if (mbase + r < q.mover_cap)
+            q.movers[(size_t)(mbase + r) * 5] = __longlong_as_double(GAP_PAD_BITS);
+      } else {
+        mused += k;
       }
     }
     if constexpr (PD != 0) {
@@ -228,7 +308,7 @@ __device__ __forceinline__ void cs_place_rows(const double *__restrict__ rows, i
 #define CS_NOSLOT (-1)
 #define CS_GLOBAL (1 << 30)
 template <int PD>
-__device__ __noinline__ int cs_reserve(int *s_nrows, int scr_rows, int *counts, double *movers,
+__device__ __forceinline__ int cs_reserve(int *s_nrows, int scr_rows, int *counts, double *movers,
                                        int mover_cap) {
   const int lane = threadIdx.x & 31;
   int slot = 0;
@@ -362,16 +442,25 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
     ixe[p] = (int)xe[p]; iye[p] = (int)ye[p]; ixb[p] = (int)xb[p]; iyb[p] = (int)yb[p];
     ok = ok && ixe[p] == c.cix && iye[p] == c.ciy;
   }
-  if (c.fast && __all_sync(SKB_FULL, ok)) {
+  if (CS_ABLATE & 4) {
+  } else if (c.fast && __all_sync(SKB_FULL, ok)) {
 #pragma unroll
     for (int p = 0; p < NP; p++) {
       double e[3], b[3];
       if constexpr (ORDER == 1) {
         const double dx = xe[p] - (double)ixe[p], tx = 1.0 - dx;
         const double dy = ye[p] - (double)iye[p], ty = 1.0 - dy;
+#if CS_HOIST_E
 #pragma unroll
         for (int k = 0; k < 3; k++)
           e[k] = dy * (dx * c.eC[3][k] + tx * c.eC[2][k]) + ty * (dx * c.eC[1][k] + tx * c.eC[0][k]);
+#else
+        const double *ep = sE + ((c.ciy - w.y0) * CS_WS + (c.cix - w.x0)) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          e[k] = dy * (dx * ep[(CS_WS + 1) * 3 + k] + tx * ep[CS_WS * 3 + k]) +
+                 ty * (dx * ep[3 + k] + tx * ep[k]);
+#endif
         const double *bp = sB + ((iyb[p] - w.y0) * CS_WS + (ixb[p] - w.x0)) * 3;
         const double dxb = xb[p] - (double)ixb[p], txb = 1.0 - dxb;
         const double dyb = yb[p] - (double)iyb[p], tyb = 1.0 - dyb;
@@ -418,7 +507,7 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
       rescale_and_kick<MODIFIED>(e, b, g, q.k, y[p], vx[p], vy[p], vz[p]);
     }
   } else {
-#pragma unroll 1
+#pragma unroll                     // (static indices: x[], y[], ... must stay in registers)
     for (int p = 0; p < NP; p++)
       if (act[p])
         fields_and_kick<ORDER, MODIFIED>(sE, sB, w, CS_WS, E, B, g, q.k, x[p], y[p], vx[p],
@@ -440,7 +529,7 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
 #pragma unroll
   for (int p = 0; p < NP; p++) leaver[p] = false;
   if (__any_sync(SKB_FULL, odd)) {
-#pragma unroll 1
+#pragma unroll
     for (int p = 0; p < NP; p++) {
       if (!act[p]) continue;
       if ((q.flags & SKB_EPI_PERIODIC_X) && !(x[p] >= 0.0 && x[p] < nxd)) x[p] = wrap_x(x[p], nxd);
@@ -479,7 +568,7 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
   bool parked[NP];
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    const bool mover = act[p] && !leaver[p] && !stay[p];
+    const bool mover = !(CS_ABLATE & 1) && act[p] && !leaver[p] && !stay[p];
     parked[p] = cs_stage_movers<PD>(mover, x[p], y[p], vx[p], vy[p], vz[p], mv, mbuf, s_nrows,
                                     scr, scr_rows, q);
     stay[p] = stay[p] || parked[p];
@@ -489,10 +578,11 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
     // compacted to the front of the cell's range: always behind the reads (everything up to
     // the end of this block is already in the ring)
     const unsigned sm = __ballot_sync(SKB_FULL, stay[p]);
-    if (stay[p]) {
+    if (stay[p] && !(CS_ABLATE & 2)) {
       double *px = P.x + ((long long)c.s + c.wcur + __popc(sm & lt));
-      px[0] = x[p]; px[pstride] = y[p]; px[2 * pstride] = vx[p]; px[3 * pstride] = vy[p];
-      px[4 * pstride] = vz[p];
+      cs_store_stream(px, x[p]); cs_store_stream(px + pstride, y[p]);
+      cs_store_stream(px + 2 * pstride, vx[p]); cs_store_stream(px + 3 * pstride, vy[p]);
+      cs_store_stream(px + 4 * pstride, vz[p]);
       if constexpr (PD != 0) {
         const double vxr = vx[p] + dq.dp.S * (y[p] * g.dy + g.y0);     // deposit.pxd:24
         if (!parked[p]) accumulate<ORDER>(c.acc, wx[p], wy[p], vxr, vy[p], vz[p]);
@@ -545,21 +635,23 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
   double *sS = sB + CS_WIN3;                                  // (PD) window of the sources
   unsigned long long *bars = (unsigned long long *)(sS + (PD ? CS_WIN4 : 0));
   __shared__ int s_blk, s_nrows;
-  __shared__ int s_nstay[CS_CELLS];
+  __shared__ int s_nstay[CS_CELLS];                // stayers of every cell (after the stream)
+  __shared__ int s_cnt[CS_CELLS];                  // live particles incl. the re-inserted rows
+  __shared__ int s_gs[CS_CELLS + 1];               // slot ranges of the CTA's cells
 
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
-  const int c0 = (tile << 8) + (half << 7);
+  const int tile = blockIdx.x / CS_PARTS, part = blockIdx.x % CS_PARTS;
+  const int c0 = (tile << 8) + part * CS_CELLS;
   const int wc0 = c0 + wv * CS_CPW;
   // my cells: lane j < 16 holds the slot range and the count of cell wc0 + j
   const int my_cnt = lane < CS_CPW ? q.gap_count[wc0 + lane] : 0;
   const int my_start = lane < CS_CPW ? q.gap_start[wc0 + lane] : 0;
   if (!__syncthreads_or(my_cnt)) return;                     // nothing lives here
   const int bx = (tile % q.key.ntx) << 4;
-  const int by = ((tile / q.key.ntx) << 4) + (half << 3);
+  const int by = ((tile / q.key.ntx) << 4) + part * CS_WARPS;
   Window w;
   w.x0 = max(bx - SKB_HALO_LO, 0); w.y0 = max(by - SKB_HALO_LO, 0);
-  w.x1 = min(bx + 16 + SKB_HALO_HI, g.mx); w.y1 = min(by + 8 + SKB_HALO_HI, g.myp);
+  w.x1 = min(bx + 16 + SKB_HALO_HI, g.mx); w.y1 = min(by + CS_WARPS + SKB_HALO_HI, g.myp);
   if (threadIdx.x == 0) {
     int b = -1;
     if (q.npool > 0) {
@@ -569,6 +661,8 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     s_blk = b; s_nrows = 0;
   }
   if (threadIdx.x < CS_CELLS) s_nstay[threadIdx.x] = 0;
+  if (lane < CS_CPW) s_gs[wv * CS_CPW + lane] = my_start;
+  if (threadIdx.x == 0) s_gs[CS_CELLS] = q.gap_start[c0 + CS_CELLS];
   const unsigned bar0 = cs_smem(bars + wv * CS_NST);
   if (lane == 0) {
 #pragma unroll
@@ -603,7 +697,7 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
 #define CS_FETCH(stage, j, base)                                                        \
   do {                                                                                  \
     const int fs_ = __shfl_sync(SKB_FULL, my_start, (j)) + (base);                      \
-    const bool big_ = CS_CNT(j) - (base) > 32;                                          \
+    const bool big_ = CS_STAGE == 64 && CS_CNT(j) - (base) > 32;                        \
     if (lane == 0) {                                                                    \
       const unsigned bar_ = bar0 + 8 * (stage);                                         \
       cs_mbar_expect_tx(bar_, big_ ? 5u * 8u * 64u : 5u * 8u * 32u);                    \
@@ -632,7 +726,7 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
       c.xsafe = (double)c.cix + 0.25 - q.k.offEx - (ORDER == 2 ? 0.5 : 0.0);
       // every stencil a particle filed under this cell can touch lies inside the window
       c.fast = c.cix - LO >= w.x0 && c.cix + 2 < w.x1 && c.ciy - LO >= w.y0 && c.ciy + 2 < w.y1;
-      if (ORDER == 1 && c.fast) {
+      if (CS_HOIST_E && ORDER == 1 && c.fast) {
         const double *eb = sE + ((c.ciy - w.y0) * CS_WS + (c.cix - w.x0)) * 3;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -650,17 +744,30 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     phases ^= 1u << stage;
     const double *pp = ring + stage * CS_STAGE_D + lane;
     const int nrem = n - cbase;
+#if CS_NP2
     if (nrem > 32)
       cs_block<ORDER, MODIFIED, PD, 2>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
                                        dq, mbuf, &s_nrows, scr, scr_rows);
     else
       cs_block<ORDER, MODIFIED, PD, 1>(pp, 32, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
                                        dq, mbuf, &s_nrows, scr, scr_rows);
+#else
+    {
+      const int pitch = (CS_STAGE == 64 && nrem > 32) ? 64 : 32;
+#pragma unroll 1
+      for (int u = 0; u < CS_STAGE / 32; u++) {
+        if (u * 32 >= nrem) break;
+        cs_block<ORDER, MODIFIED, PD, 1>(pp + u * 32, pitch, nrem - u * 32, c, mv, P, pstride, sE,
+                                         sB, sS, w, E, B, g, q, dq, mbuf, &s_nrows, scr,
+                                         scr_rows);
+      }
+    }
+#endif
     __syncwarp();                                  // stage fully read: refill it
     int nj = cj, nbase = cbase;
     CS_ADVANCE(nj, nbase);
     if (nj != cj) {                                // the cell is finished
-      if (lane == 0) { q.gap_count[wc0 + cj] = c.wcur; s_nstay[wv * CS_CPW + cj] = c.wcur; }
+      if (lane == 0) s_nstay[wv * CS_CPW + cj] = c.wcur;
       c.wcur = 0;
       if constexpr (PD != 0) cs_emit_cell<NS>(c.acc, c.fast, sS, w, dq.cur, g);
     }
@@ -688,21 +795,29 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
   if (lane == 0) cs_bulk_wait_all();               // my scratch rows are in memory
   // phase B: all cells of this CTA are compacted; place the parked rows
   __syncthreads();
+  if (threadIdx.x < CS_CELLS) s_cnt[threadIdx.x] = s_nstay[threadIdx.x];
+  __syncthreads();
   const int nrows = min(s_nrows, scr_rows);        // (reservations are whole halves)
-  if (nrows > 0) {
+  if (nrows > 0 && !(CS_ABLATE & 8)) {
     if (threadIdx.x == 0) atomicAdd(q.counts + 4, nrows);            // statistics
+    int mbase = 0, mused = GAP_MCHUNK;             // this warp's chunk of the global list
+    // the rows were written ~100 us ago and have mostly left L2: pull them all back at
+    // once instead of paying the HBM latency once per batch
+    for (int i = (int)threadIdx.x * 16; i < nrows * 5; i += CS_THREADS * 16)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(scr + i));
     for (int r0 = 0; r0 < nrows; r0 += CS_THREADS * GAP_INS_ITEMS)
-      cs_place_rows<ORDER, PD>(scr, nrows, r0 + (int)threadIdx.x, P, q, dq, g, w, sS, c0);
+      cs_place_rows<ORDER, PD>(scr, nrows, r0 + (int)threadIdx.x, P, q, dq, g, w, sS, c0, mbase,
+                               mused, s_gs, s_cnt);
   }
   __syncthreads();
+  if (threadIdx.x < CS_CELLS) q.gap_count[c0 + threadIdx.x] = s_cnt[threadIdx.x];
   if (threadIdx.x == 0 && s_blk >= 0) atomicExch(q.pool_owner + s_blk, 0);
   if constexpr (PD != 0) {
     // the rows re-inserted above sit behind the stayers of their cells: accumulate them
     // like the stayers (same cell => same stencil), one reduction + emit per cell
     for (int j = 0; j < CS_CPW; j++) {
-      const int cell = wc0 + j;
       const int n0 = s_nstay[wv * CS_CPW + j];
-      const int n1 = __ldcg(q.gap_count + cell);
+      const int n1 = s_cnt[wv * CS_CPW + j];
       if (n1 <= n0) continue;
       const int st = __shfl_sync(SKB_FULL, my_start, j);
       const int ax = bx + j;
@@ -810,7 +925,7 @@ int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const
     }
     if (q.npool < resident[slot]) return (int)cudaErrorInvalidValue;
   }
-  k<<<ntiles * 2, CS_THREADS, smem, st>>>(tm64, tm32, p, stride, E, B, g, q, dq);
+  k<<<ntiles * CS_PARTS, CS_THREADS, smem, st>>>(tm64, tm32, p, stride, E, B, g, q, dq);
   SKB_CHECK_LAUNCH();
   return 0;
 }

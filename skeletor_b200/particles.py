@@ -361,11 +361,11 @@ class Particles:
         if self._gap_fail is not None and \
                 abs(self.N - self._gap_fail) <= 0.02*self._gap_fail:
             return False        # did not fit last time and N has hardly changed
-        if self._gap_thrash >= 4:
+        if self._gap_thrash >= 16:
             # the caller reads the particles after every push: converting back and forth
             # costs more than the tile sort; try again every 64 pushes
             self._gap_thrash += 1
-            if self._gap_thrash < 68:
+            if self._gap_thrash < 80:
                 return False
             self._gap_thrash = 0
         if not (self._sorted and self._n_sorted == self.N):
@@ -497,6 +497,7 @@ class Particles:
         src.boundaries_set = False
         src.normalize(self)
         src.set_boundaries()
+        self._gap_pushes += 1
         cfl = had_leftovers and int(self.ihole[0].item()) < 0
         if update:
             self._gap_finish(cnt, cfl)

@@ -30,7 +30,7 @@ def namespace(gapped=False):
         """same scenarios on the gapped particle layout (room for the slot ranges)"""
 
         def __init__(self, manifold, Nmax, **kw):
-            super().__init__(manifold, 4*int(Nmax), **kw)
+            super().__init__(manifold, 4*int(Nmax) + 8192, **kw)   # (empty cells own 4 slots each)
             self.gapped = True
 
         def _gap_finish(self, cnt, *args, **kw):

@@ -58,6 +58,11 @@ def parse():
                     help="5 %% sinusoidal density contrast along x (SURVEY.md 8d)")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: ny grows with the GPU count (ny rows PER GPU)")
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 5 (default, the one the metric is quoted on) "
+                         "uniform plasma push+deposit; 2 Landau loop incl. Ohm, 1024^2 x 64 "
+                         "ppc; 3 Horowitz iterate, 2048^2 x 128 ppc, Hall Ohm + Faraday; 4 "
+                         "shearing sheet (push_modified + sheared guards), 2048^2 x 256 ppc")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true",
@@ -203,7 +208,7 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------
-def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
+def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8, modified=False):
     """Parity at BENCH SCALE and at N ranks, through the public API, against the oracle
     (checker only; runs after the timed region).
 
@@ -227,7 +232,9 @@ def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
     rank, size = comm.rank, comm.size
     dev = ions.device
     order = ions.order
-    og = orc.Grid(a.nx, a.ny, rank=rank, size=size, lbx=m.lbx, lby=m.lby, Lx=m.Lx, Ly=m.Ly)
+    S, Omega = getattr(m, "S", None), getattr(m, "Omega", None)
+    og = orc.Grid(a.nx, a.ny, rank=rank, size=size, lbx=m.lbx, lby=m.lby, Lx=m.Lx, Ly=m.Ly,
+                  x0=m.x0, y0=m.y0, S=S, Omega=Omega)
     Eh = np.ascontiguousarray(np.asarray(E)).view(orc.Float3).reshape(m.myp, m.mx)
     Bh = np.ascontiguousarray(np.asarray(B)).view(orc.Float3).reshape(m.myp, m.mx)
 
@@ -240,7 +247,13 @@ def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
     rows = ions._data[:, idx].t().contiguous().cpu().numpy()
     part = np.ascontiguousarray(rows).view(orc.Particle).reshape(-1).copy()
     qtmh = ions.charge/ions.mass*dt/2
-    orc.push(part, Eh, Bh, og, order, qtmh, dt)
+    if modified:
+        orc.push(part, Eh, Bh, og, order, qtmh, dt, True, float(Omega), float(S))
+    else:
+        orc.push(part, Eh, Bh, og, order, qtmh, dt)
+    if S is not None:
+        # shear_periodic_y with the particle time AFTER the push (particles.py:154-155,175)
+        orc.shear_periodic_y(part, og, float(S), float(ions.time) + dt)
     # periodic_y: cppmove2 wraps on the edge ranks (pplib2.c:676-677, 692-693); with
     # |vy dt/dy| << nyp nobody moves more than one slab, so only they can cross 0 / ny
     y = part["y"]
@@ -253,9 +266,10 @@ def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
         exp_rows = np.concatenate(comm.allgather(exp_rows))
 
     # ---- one more step on the GPUs -----------------------------------------------------
-    ions.push(E, B, dt)
+    (ions.push_modified if modified else ions.push)(E, B, dt)
     src.deposit(ions)
     src_raw = src.t.clone()             # normalised, guards not folded yet
+    src.time = ions.time
     src.add_guards()
     src.copy_guards()
 
@@ -292,7 +306,7 @@ def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8):
     lo_i, hi_i = r0 - 1, (r1 if order == 1 else r1 + 1)     # stencil-base rows that touch it
     sel = []
     for s0 in range(0, N, CH):
-        iy = (ions._data[1, s0:s0 + CH] + offy).to(torch.int32)
+        iy = (ions._data[1, s0:min(s0 + CH, N)] + offy).to(torch.int32)
         k = ((iy >= lo_i) & (iy < hi_i)).nonzero().squeeze(1)
         if k.numel():
             sel.append(ions._data[:, s0 + k].t().contiguous().cpu())
@@ -687,12 +701,209 @@ def b200_arm(a):
         print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------
+CONFIGS = {
+    2: dict(nx=1024, ny=1024, ppc=64, what="Landau / ion-acoustic loop (BASELINE config 2): "
+            "push + deposit + add_guards + copy_guards + Ohm + copy_guards per step"),
+    3: dict(nx=2048, ny=2048, ppc=121, what="hybrid stepper (BASELINE config 3): one Horowitz "
+            "iterate per step = push_and_deposit sweep + Faraday/Hall-Ohm iterations, "
+            "B = x-hat, lbx = lby = 2, quiet start 11 x 11 per cell"),
+    4: dict(nx=2048, ny=2048, ppc=256, what="shearing sheet (BASELINE config 4): push_modified "
+            "(S = -3/2, Omega = 1) + deposit + shear-periodic add_guards / copy_guards per "
+            "step"),
+}
+
+
+def config_arm(a):
+    """BASELINE.json configs 2-4 in the same JSON format (config 5 = b200_arm): whole-step
+    timing, live roofline of the particle kernel, parity / conservation checks."""
+    import numpy as np
+    import torch
+    import skeletor_b200 as sk
+    from skeletor_b200 import _lib
+
+    c = CONFIGS[a.config]
+    if a.nx == NX and a.ny == NY and a.ppc == PPC:       # not overridden on the command line
+        a.nx, a.ny, a.ppc = c["nx"], c["ny"], c["ppc"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    comm = sk.COMM_WORLD if world > 1 else sk.COMM_SELF
+    rank, size = comm.rank, comm.size
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lb = 1 if a.config == 2 else 2
+    if a.config == 4:
+        m = sk.ShearingManifold(a.nx, a.ny, comm, lbx=lb, lby=lb, S=-1.5, Omega=1.0,
+                                Lx=1.0, Ly=a.ny/a.nx)
+    elif a.config == 3:
+        m = sk.Manifold(a.nx, a.ny, comm, lbx=lb, lby=lb, Lx=0.5*a.nx, Ly=0.5*a.ny)
+    else:
+        m = sk.Manifold(a.nx, a.ny, comm, lbx=lb, lby=lb, Lx=1.0, Ly=a.ny/a.nx)
+    n_local = a.nx*m.nyp*a.ppc
+    n_total = a.nx*a.ny*a.ppc
+    nmax = int(1.36*n_local) + 4096
+    nmax += nmax & 1
+    ions = sk.Particles(m, nmax, charge=1.0, mass=1.0, order=1,
+                        nbmax=max(n_local//100, 1 << 16))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    d = ions._data
+    if a.config == 3:
+        # quiet start: sq x sq sub-lattice per cell, cold-ish ions (a noisy start drives
+        # O(1) electric fields through grad ln(rho) in the Hall / pressure terms)
+        sq = int(round(a.ppc**0.5))
+        assert sq*sq == a.ppc, "config 3 needs a square number of particles per cell"
+        ax = (torch.arange(a.nx*sq, device=dev, dtype=torch.float64) + 0.5)/sq
+        ay = m.noff + (torch.arange(m.nyp*sq, device=dev, dtype=torch.float64) + 0.5)/sq
+        d[0, :n_local] = ax.repeat(m.nyp*sq)
+        d[1, :n_local] = ay.repeat_interleave(a.nx*sq)
+        d[2:5, :n_local] = 0.1*torch.randn((3, n_local), generator=gen, device=dev,
+                                           dtype=torch.float64)
+    else:
+        d[0, :n_local] = torch.rand(n_local, generator=gen, device=dev,
+                                    dtype=torch.float64)*a.nx
+        d[1, :n_local] = m.noff + torch.rand(n_local, generator=gen, device=dev,
+                                             dtype=torch.float64)*m.nyp
+        vt = 0.05 if a.config == 4 else 1.0
+        d[2:5, :n_local] = vt*torch.randn((3, n_local), generator=gen, device=dev,
+                                          dtype=torch.float64)
+    ions.N = n_local
+    E = sk.Field(m, dtype=sk.Float3)
+    B = sk.Field(m, dtype=sk.Float3)
+    src = sk.Sources(m)
+    hot = ["skb_push_gapped", "skb_boris_push", "skb_deposit", "skb_push_and_deposit_gapped",
+           "skb_push_and_deposit"]
+    stepper = None
+    if a.config == 2:
+        dt = 0.1*m.dx
+        E.copy_guards(); B.copy_guards()
+        ohm = sk.Ohm(m, temperature=1.0, charge=1.0)
+        src.deposit(ions, set_boundaries=True)
+
+        def step():
+            ions.push(E, B, dt)
+            src.deposit(ions)
+            src.add_guards()
+            src.copy_guards()
+            ohm(src, B, E)
+            E.copy_guards()
+        sweep_bytes, dom_ep = 120.0, "skb_push_gapped"
+    elif a.config == 4:
+        dt = 0.1*m.dx
+        xg, yg = np.meshgrid(m.x, m.y)
+        E['x'].active = 0.01*np.sin(2*np.pi*xg/m.Lx)
+        B['z'].active = 1.0
+        E.copy_guards(); B.copy_guards()
+
+        def step():
+            ions.push_modified(E, B, dt)
+            src.deposit(ions)
+            src.time = ions.time
+            src.add_guards()
+            src.copy_guards()
+        sweep_bytes, dom_ep = 120.0, "skb_push_gapped"
+    else:
+        from skeletor_b200.time_steppers.horowitz import TimeStepper as Horowitz
+        dt = 1e-2
+        B.fill((1.0, 0.0, 0.0))
+        B.copy_guards()
+        stepper = Horowitz(sk.State(ions, B), sk.Ohm(m, temperature=0.01, charge=1.0), m)
+        # (no prepare(): the iteration to t = 0 consistency is set-up, not the step)
+        ions.deposit(set_boundaries=True)
+        stepper.sources.t.copy_(ions.sources.t)
+        stepper.sources.boundaries_set = True
+        stepper.ohm(stepper.sources, stepper.B, stepper.E, set_boundaries=True)
+
+        def step():
+            stepper.iterate(dt)
+        sweep_bytes, dom_ep = 80.0, "skb_push_and_deposit_gapped"
+
+    def barrier():
+        if size > 1:
+            comm.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if size > 1:
+            ms = comm.allreduce(ms, op=sk.comm.MAX)
+        return ms
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    k0 = _lib.kernel_launches
+    _lib.trace = {k: [] for k in hot}
+    ms = timed(step, a.steps)
+    live = {k: [e0.elapsed_time(e1) for e0, e1 in v] for k, v in _lib.trace.items() if v}
+    _lib.trace = None
+    launches = _lib.kernel_launches - k0
+    clk = clocks.stop() if rank == 0 else None
+    value = n_total*a.steps/(ms*1e-3)
+    peak, peak_src = measured_peak()
+    npart = int(ions.N)
+    cells = m.mx*m.myp
+    alg = {"skb_push_gapped": 80.0*npart + 48.0*cells, "skb_boris_push": 80.0*npart + 48.0*cells,
+           "skb_deposit": 40.0*npart + 32.0*cells,
+           "skb_push_and_deposit_gapped": 80.0*npart + 80.0*cells,
+           "skb_push_and_deposit": 80.0*npart + 80.0*cells}
+    kern = {}
+    for ep, ts in live.items():
+        ts = [t for t in ts if t > 0.2*max(ts)]
+        avg = sum(ts)/len(ts)
+        kern[ep] = {"live_ms": round(avg, 4), "live_launches": len(ts),
+                    "launches_per_step": round(len(ts)/a.steps, 2),
+                    "alg_bytes": alg[ep],
+                    "live_frac": round(alg[ep]/(avg*1e-3)/1e9/peak, 4)}
+    dom = dom_ep if dom_ep in kern else max(kern, key=lambda k: kern[k]["live_ms"])
+    dk = kern[dom]
+    roofline = {"kernel": dom, "bound": "hbm",
+                "achieved": round(dk["alg_bytes"]/(dk["live_ms"]*1e-3)/1e9, 1), "peak": peak,
+                "unit": "GB/s", "frac": dk["live_frac"], "traffic": None,
+                "peak_source": peak_src, "alg_bytes_per_launch": dk["alg_bytes"],
+                "ms_per_launch": dk["live_ms"],
+                "timing": "CUDA events around the launch in every timed step, average",
+                "step_bytes_per_particle": sweep_bytes,
+                "step_frac": round(sweep_bytes*npart/(ms/a.steps*1e-3)/1e9/peak, 4),
+                "others": {k: v for k, v in kern.items() if k != dom}}
+    checks = {}
+    if a.config in (2, 4) and not a.no_parity:
+        checks.update(parity_checks(sk, ions, E, B, src, dt, comm, a,
+                                    modified=a.config == 4))
+    n_now = comm.allreduce(int(ions.N), op=sk.comm.SUM) if size > 1 else int(ions.N)
+    checks["particles_conserved"] = n_now == n_total
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms/a.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": c["what"], "baseline_config": a.config,
+                           "grid": [a.nx, a.ny], "ppc": a.ppc, "particles": n_total,
+                           "interpolation": "CIC", "decomposition": "y-slabs, 1 per GPU",
+                           "particles_per_gpu": n_local, "layout": ions._rep,
+                           "l2_policy": "inputs larger than L2"},
+                "roofline": roofline, "kernels": kern, "cpu_baseline": None, "e2e": None,
+                "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse()
     if a.weak:
         a.ny = a.ny*max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if a.impl == "reference":
         reference_arm(a)
+    elif a.config != 5:
+        config_arm(a)
     else:
         b200_arm(a)
 

@@ -136,10 +136,11 @@ int skb_calculate_ihole(skb_particles_t p, long long np, int *ihole, int ntmax,
  *   the hole count from ihole[0] on the device" (no host round trip between push and
  *   pack); it is echoed into counts[3].
  * skb_move_classify: multi-hop support (pplib2.c:756-866): split a received
- *   buffer into particles that belong here (copied to `keep`, count in
- *   counts[0]) and particles to pass further down / up (appended to sbufl /
- *   sbufr with the edge-rank y wrap; counts[1], counts[2]; counts[3] = overflow).
- *   The caller zeroes counts[0..3].  nrecv = -(capacity + 1): header mode for the
+ *   buffer into particles that belong here (copied to `keep`, 2 * nbmax rows; count in
+ *   counts[0], which may carry on from earlier calls) and particles to pass further
+ *   down / up (appended to sbufl / sbufr with the edge-rank y wrap; counts[1],
+ *   counts[2]; counts[3] = overflow of any of the three buffers, rows beyond the
+ *   capacity are not written).  The caller zeroes counts[1..3].  nrecv = -(capacity + 1): header mode for the
  *   peer-memory exchange — the row count is the first double of rbuf and the rows
  *   follow a 5-double header.
  * skb_move_unpack: put `nin` incoming particles (AoS rows in `in`) into the

@@ -161,8 +161,11 @@ move_classify_kernel(const double *__restrict__ rbuf, int nrecv, double *keep,
       if (slot < nbmax) put_row(sbufr, slot, r[0], y, r[2], r[3], r[4]);
       else counts[3] = 1;
     } else {
+      // keep holds 2 * nbmax rows (both neighbours' buffers can arrive full); the count
+      // runs on across forwarding rounds, so it is checked like the send buffers
       int slot = atomicAdd(counts + 0, 1);
-      put_row(keep, slot, r[0], y, r[2], r[3], r[4]);
+      if (slot < 2 * nbmax) put_row(keep, slot, r[0], y, r[2], r[3], r[4]);
+      else counts[3] = 1;
     }
   }
 }

@@ -166,8 +166,12 @@ class Particles:
         # the push also accumulates the stencil sums of the new positions into a private
         # grid and Sources.deposit(ions) picks that grid up when the particles have not
         # been touched in between.  "auto": switched on by the first deposit that follows a
-        # push, switched off again when a fused result goes unused.
-        self.fuse_deposit = os.environ.get("SKELETOR_B200_FUSE", "auto")
+        # push, switched off again when a fused result goes unused.  OFF by default: on
+        # config 5 the fused sweep takes 50 ms against 23.7 + 7.5 ms for the two kernels
+        # (register pressure of the two roles in one kernel).  OFF by default: on
+        # config 5 the fused sweep takes 50 ms against 23.7 + 7.5 ms for the two kernels
+        # (register pressure of the two roles in one kernel).
+        self.fuse_deposit = os.environ.get("SKELETOR_B200_FUSE", "0")
         if self.fuse_deposit in ("0", "1"):
             self.fuse_deposit = self.fuse_deposit == "1"
         self._fuse_next = False

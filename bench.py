@@ -875,6 +875,7 @@ def config_arm(a):
                 "step_bytes_per_particle": sweep_bytes,
                 "step_frac": round(sweep_bytes*npart/(ms/a.steps*1e-3)/1e9/peak, 4),
                 "others": {k: v for k, v in kern.items() if k != dom}}
+    layout = ions._rep
     checks = {}
     if a.config in (2, 4) and not a.no_parity:
         checks.update(parity_checks(sk, ions, E, B, src, dt, comm, a,
@@ -889,7 +890,7 @@ def config_arm(a):
                 "config": {"workload": c["what"], "baseline_config": a.config,
                            "grid": [a.nx, a.ny], "ppc": a.ppc, "particles": n_total,
                            "interpolation": "CIC", "decomposition": "y-slabs, 1 per GPU",
-                           "particles_per_gpu": n_local, "layout": ions._rep,
+                           "particles_per_gpu": n_local, "layout": layout,
                            "l2_policy": "inputs larger than L2"},
                 "roofline": roofline, "kernels": kern, "cpu_baseline": None, "e2e": None,
                 "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}

@@ -390,6 +390,43 @@ int skb_ohm(const double *sources, const double *B, double *E, double *Je_out,
 /* Faraday.__call__ (faraday.py:16-30): B -= dt * curl_up(E) on active cells */
 int skb_faraday(const double *E, double *B, double *dB_out,
                 const skb_grid_t *grid, double dt, void *stream);
+/* ---- time-stepper field algebra on the device (horowitz.py:138-169) ------------------
+ * Every call takes `skip` (device int, may be NULL): the kernel does nothing when *skip
+ * != 0, so the iterations of the Horowitz loop can be queued ahead of the convergence
+ * test.
+ * skb_field_combine: out = c*(x + y) (mode 0: E2 = 0.5*(E3 + E), B2 = 0.5*(B3 + B)) or
+ *   out = -x + c*y (mode 1), n doubles.
+ * skb_faraday_to:    Bout = Bin - dt*curl_up(E) on the active cells ("B3 = B; faraday(E2,
+ *   B3, dt)", horowitz.py:147-148, faraday.py:16-30).
+ * skb_ohm_if:        skb_ohm with the skip flag.
+ * skb_horowitz_update: E3 <- -E + 2*E2 (whole array) and acc[0] += sum over active cells
+ *   and components of (E3_new - E3_old)^2 (calculate_diff, horowitz.py:112-121).
+ * skb_converged:     state[0] = 1, state[1] = iter when sqrt(acc[0]*scale) < tol (and not
+ *   already set). */
+int skb_field_combine(double *out, const double *x, const double *y, long long n, double c,
+                      int mode, const int *skip, void *stream);
+int skb_faraday_to(const double *E, const double *Bin, double *Bout, double *dB_out,
+                   const skb_grid_t *grid, double dt, const int *skip, void *stream);
+int skb_ohm_if(const double *sources, const double *B, double *E, double *Je_out,
+               double *Bc_out, const skb_grid_t *grid, double alpha, double eta,
+               const int *skip, void *stream);
+int skb_horowitz_update(double *E3, const double *E, const double *E2, const skb_grid_t *grid,
+                        double *acc, const int *skip, void *stream);
+int skb_converged(const double *acc, double scale, double tol, int iter, int *state,
+                  void *stream);
+
+/* ---- electrostatic field solve, k-space part -------------------------------------------
+ * calc_form_factors + grad_inv_del (operators.pyx:13-135; ppic2's cppois22,
+ * ppic2_wrapper.pyx:100-116) on the spectrum of a cuFFT real-to-complex transform:
+ * q, fx, fy = [ny][nx/2+1] complex128.  fx, fy = -i k S(k)/k^2 q with the modes the
+ * reference zeroes; *we += field energy (operators.pyx:135; zeroed by the caller, may be
+ * NULL).  float32_quirk != 0 reproduces the reference's crealf / cimagf truncation
+ * (SURVEY.md Q3).  The transforms themselves (cwpfft2rinit / cwppfft2r / cwppfft2r2,
+ * ppic2_wrapper.pyx:69-142) are cuFFT calls of the host side. */
+int skb_poisson_kspace(const double *q, double *fx, double *fy, int nx, int ny, double Lx,
+                       double Ly, double ax, double ay, double affp, int float32_quirk,
+                       double *we, void *stream);
+
 
 #ifdef __cplusplus
 }

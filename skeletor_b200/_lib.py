@@ -109,6 +109,13 @@ SIGNATURES = {
     "skb_interp": [c_vp, c_vp, c_vp, c_int, c_vp, _G, c_int, c_vp],
     "skb_ohm": [c_vp, c_vp, c_vp, c_vp, c_vp, _G, c_dbl, c_dbl, c_vp],
     "skb_faraday": [c_vp, c_vp, c_vp, _G, c_dbl, c_vp],
+    "skb_field_combine": [c_vp, c_vp, c_vp, c_ll, c_dbl, c_int, c_vp, c_vp],
+    "skb_faraday_to": [c_vp, c_vp, c_vp, c_vp, _G, c_dbl, c_vp, c_vp],
+    "skb_ohm_if": [c_vp, c_vp, c_vp, c_vp, c_vp, _G, c_dbl, c_dbl, c_vp, c_vp],
+    "skb_horowitz_update": [c_vp, c_vp, c_vp, _G, c_vp, c_vp, c_vp],
+    "skb_converged": [c_vp, c_dbl, c_dbl, c_int, c_vp, c_vp],
+    "skb_poisson_kspace": [c_vp, c_vp, c_vp, c_int, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
+                           c_int, c_vp, c_vp],
 }
 OTHER = {
     "skb_version": ([], c_int),

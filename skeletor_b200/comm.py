@@ -33,6 +33,11 @@ class SelfComm:
     def allgather(self, x):
         return [x]
 
+    def allreduce_tensor_(self, t, op=SUM):
+        """in-place reduction of a device tensor over the ranks, ordered on the current
+        stream (no host round trip)"""
+        return t
+
     def gather(self, x, root=0):
         return [x]
 
@@ -96,6 +101,39 @@ class TorchComm:
         if scalar:
             return int(out) if dt == torch.int64 else float(out)
         return out
+
+    def allgather_tensor(self, t):
+        """concatenation (dim 0) of every rank's equally shaped device tensor, on the
+        device: NCCL all-gather; host-staged over gloo"""
+        import torch
+        dist = self._dist
+        t = t.contiguous()
+        out = torch.empty((self.size*t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype,
+                          device=t.device)
+        if self.backend == "nccl":
+            dist.all_gather_into_tensor(out, t, group=self.group)
+        elif not t.is_cuda:
+            parts = [torch.empty_like(t) for _ in range(self.size)]
+            dist.all_gather(parts, t, group=self.group)
+            out.copy_(torch.cat(parts))
+        else:
+            parts = [torch.empty(t.shape, dtype=t.dtype) for _ in range(self.size)]
+            dist.all_gather(parts, t.cpu(), group=self.group)
+            out.copy_(torch.cat(parts))
+        return out
+
+    def allreduce_tensor_(self, t, op=SUM):
+        """in-place reduction of a device tensor over the ranks: NCCL on the current
+        stream (no host round trip); host-staged over gloo"""
+        dist = self._dist
+        rop = {SUM: dist.ReduceOp.SUM, MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN}[op]
+        if self.backend == "nccl" or not t.is_cuda:
+            dist.all_reduce(t, op=rop, group=self.group)
+        else:
+            h = t.cpu()
+            dist.all_reduce(h, op=rop, group=self.group)
+            t.copy_(h)
+        return t
 
     def allgather(self, x):
         out = [None]*self.size

@@ -99,8 +99,10 @@ interp_kernel(Plane fx, Plane fy, Plane fz, double *out, DevGrid g, int up) {
 // ohm.py:35-75 in one pass.  src = Float4 (rho, Jx, Jy, Jz), B = Float3.
 __global__ void __launch_bounds__(ST)
 ohm_kernel(const double *__restrict__ src, const double *__restrict__ B, double *E,
-           double *Je_out, double *Bc_out, DevGrid g, double alpha, double eta) {
+           double *Je_out, double *Bc_out, DevGrid g, double alpha, double eta,
+           const int *skip) {
   int iy, ix;
+  if (skip && *skip) return;                  // (device-side loop control of the steppers)
   if (!active_cell(g, iy, ix)) return;
   const Plane rho{src, 4, g.mx};
   const Plane bx{B, 3, g.mx}, by{B + 1, 3, g.mx}, bz{B + 2, 3, g.mx};
@@ -136,20 +138,23 @@ ohm_kernel(const double *__restrict__ src, const double *__restrict__ B, double 
 }
 
 // faraday.py:16-30: B -= curl_up(E)*dt.  E (with guards) is read-only, B is updated
-// in place cell by cell.
+// cell by cell: in place (Bin == B) or from a second field (B = Bin - curl_up(E)*dt, the
+// "B3 = B; faraday(E2, B3, dt)" of horowitz.py:147-148 in one pass).
 __global__ void __launch_bounds__(ST)
-faraday_kernel(const double *__restrict__ E, double *B, double *dB_out, DevGrid g,
-               double dt) {
+faraday_kernel(const double *__restrict__ E, const double *Bin, double *B, double *dB_out,
+               DevGrid g, double dt, const int *skip) {
   int iy, ix;
+  if (skip && *skip) return;
   if (!active_cell(g, iy, ix)) return;
   const Plane ex{E, 3, g.mx}, ey{E + 1, 3, g.mx}, ez{E + 2, 3, g.mx};
   const double cx = ddyup(ez, ix, iy, g.dy);
   const double cy = -ddxup(ez, ix, iy, g.dx);
   const double cz = ddxup(ey, ix, iy, g.dx) - ddyup(ex, ix, iy, g.dy);
   double *b = B + ((size_t)iy * g.mx + ix) * 3;
-  b[0] = b[0] - cx * dt;
-  b[1] = b[1] - cy * dt;
-  b[2] = b[2] - cz * dt;
+  const double *bi = Bin + ((size_t)iy * g.mx + ix) * 3;
+  b[0] = bi[0] - cx * dt;
+  b[1] = bi[1] - cy * dt;
+  b[2] = bi[2] - cz * dt;
   if (dB_out) { double *q = dB_out + ((size_t)iy * g.mx + ix) * 3; q[0] = cx; q[1] = cy; q[2] = cz; }
 }
 
@@ -197,7 +202,7 @@ extern "C" int skb_ohm(const double *sources, const double *B, double *E, double
                        void *stream) {
   DevGrid g = make_grid(grid);
   ohm_kernel<<<sblk(g), ST, 0, (cudaStream_t)stream>>>(sources, B, E, Je_out, Bc_out, g,
-                                                       alpha, eta);
+                                                       alpha, eta, nullptr);
   SKB_CHECK_LAUNCH();
   return 0;
 }
@@ -205,7 +210,112 @@ extern "C" int skb_ohm(const double *sources, const double *B, double *E, double
 extern "C" int skb_faraday(const double *E, double *B, double *dB_out,
                            const skb_grid_t *grid, double dt, void *stream) {
   DevGrid g = make_grid(grid);
-  faraday_kernel<<<sblk(g), ST, 0, (cudaStream_t)stream>>>(E, B, dB_out, g, dt);
+  faraday_kernel<<<sblk(g), ST, 0, (cudaStream_t)stream>>>(E, B, B, dB_out, g, dt, nullptr);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- field algebra of the time steppers on the device ---------------------------------
+// The Horowitz iteration (horowitz.py:138-169) is a handful of whole-field averages
+// around one Faraday and one Ohm solve, repeated until the electric field stops changing.
+// In the reference every step is a NumPy pass and the convergence test a host decision.
+// Here the averages are fused kernels, the residual is reduced on the device, and every
+// kernel of an iteration takes a `skip` flag (state[0]) that skb_converged raises - so
+// several iterations can be queued without a host round trip; the ones behind the
+// converged one do nothing.
+__global__ void __launch_bounds__(256)
+combine_kernel(double *out, const double *__restrict__ x, const double *__restrict__ y,
+               long long n, double c, int mode, const int *skip) {
+  if (skip && *skip) return;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  // mode 0: c*(x + y) (E2 = 0.5*(E3 + E), horowitz.py:142); mode 1: -x + c*y
+  // (E3 = -E + 2*E2, :159)
+  out[i] = mode == 0 ? c * (x[i] + y[i]) : (-x[i]) + c * y[i];
+}
+
+// E3 <- -E + 2*E2 over the whole array (horowitz.py:159) and acc[0] += sum over the active
+// cells and the three components of (E3_new - E3_old)^2 (calculate_diff, :112-121, before
+// the mean / allreduce / sqrt)
+__global__ void __launch_bounds__(256)
+horowitz_update_kernel(double *E3, const double *__restrict__ E, const double *__restrict__ E2,
+                       DevGrid g, double *acc, const int *skip) {
+  if (skip && *skip) return;
+  const long long ncell = (long long)g.mx * g.myp;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  double d2 = 0.0;
+  if (i < ncell) {
+    const int iy = (int)(i / g.mx), ix = (int)(i - (long long)iy * g.mx);
+    const bool active = iy >= g.lby && iy < g.uby && ix >= g.lbx && ix < g.ubx;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double old = E3[i * 3 + k];
+      const double nw = (-E[i * 3 + k]) + 2.0 * E2[i * 3 + k];
+      E3[i * 3 + k] = nw;
+      if (active) { const double d = nw - old; d2 += d * d; }
+    }
+  }
+  // block sum -> one atomic per block
+  __shared__ double part[8];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) d2 += __shfl_down_sync(0xffffffffu, d2, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; k++) t += part[k];
+    if (t != 0.0) atomicAdd(acc, t);
+  }
+}
+
+__global__ void converged_kernel(const double *acc, double scale, double tol, int iter,
+                                 int *state) {
+  if (state[0]) return;
+  if (sqrt(acc[0] * scale) < tol) { state[0] = 1; state[1] = iter; }
+}
+
+extern "C" int skb_field_combine(double *out, const double *x, const double *y, long long n,
+                                 double c, int mode, const int *skip, void *stream) {
+  if (n <= 0) return 0;
+  combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, x, y, n, c,
+                                                                                 mode, skip);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_faraday_to(const double *E, const double *Bin, double *Bout, double *dB_out,
+                              const skb_grid_t *grid, double dt, const int *skip,
+                              void *stream) {
+  DevGrid g = make_grid(grid);
+  faraday_kernel<<<sblk(g), ST, 0, (cudaStream_t)stream>>>(E, Bin, Bout, dB_out, g, dt, skip);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_ohm_if(const double *sources, const double *B, double *E, double *Je_out,
+                          double *Bc_out, const skb_grid_t *grid, double alpha, double eta,
+                          const int *skip, void *stream) {
+  DevGrid g = make_grid(grid);
+  ohm_kernel<<<sblk(g), ST, 0, (cudaStream_t)stream>>>(sources, B, E, Je_out, Bc_out, g,
+                                                       alpha, eta, skip);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_horowitz_update(double *E3, const double *E, const double *E2,
+                                   const skb_grid_t *grid, double *acc, const int *skip,
+                                   void *stream) {
+  DevGrid g = make_grid(grid);
+  const long long ncell = (long long)g.mx * g.myp;
+  horowitz_update_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      E3, E, E2, g, acc, skip);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int skb_converged(const double *acc, double scale, double tol, int iter, int *state,
+                             void *stream) {
+  converged_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(acc, scale, tol, iter, state);
   SKB_CHECK_LAUNCH();
   return 0;
 }

@@ -1,5 +1,7 @@
-"""Host-side particle loading (reference skeletor/initial_condition.py:4-62): runs
-once, on the host with NumPy, then uploads — out of the hot path by design."""
+"""Particle loading (reference skeletor/initial_condition.py:4-143).  Default: on the
+host with NumPy (the reference's tests seed np.random), then uploaded.  on_device=True:
+quiet / noisy start and the density perturbation are generated in device memory - what
+a 1e9-particle start needs."""
 import numpy as np
 
 
@@ -35,17 +37,31 @@ class InitialCondition:
         return x, y
 
     def _call_on_device(self, manifold, ions):
+        """Coordinates generated straight into device memory (per-slab start): the quiet
+        start's sub-lattice is the same float64 arithmetic as `positions` (bit-identical
+        coordinates, initial_condition.py:24-30); noisy positions and the Maxwellian
+        velocities come from the GPU's generator (seed + rank)."""
         import torch
-        assert not self.quiet and not self.global_init, \
-            "on_device supports the noisy per-slab start only"
-        N = manifold.nx*manifold.nyp*self.npc
-        gen = torch.Generator(device=ions.device)
+        assert not self.global_init, "on_device initialises every slab on its own rank"
+        nx, nyp = manifold.nx, manifold.nyp
+        N = nx*nyp*self.npc
+        dev = ions.device
+        gen = torch.Generator(device=dev)
         gen.manual_seed((self.seed if self.seed is not None else 0) + manifold.comm.rank)
-        kw = dict(generator=gen, device=ions.device, dtype=torch.float64)
+        kw = dict(generator=gen, device=dev, dtype=torch.float64)
         ions._rep = "dense"           # (whatever was stored before is discarded)
         d = ions._data
-        d[0, :N] = torch.rand(N, **kw)*manifold.nx
-        d[1, :N] = torch.rand(N, **kw)*manifold.nyp + manifold.edges[0]
+        if self.quiet:
+            sq = int(np.sqrt(self.npc))
+            assert sq**2 == self.npc
+            x1 = (torch.arange(nx*sq, device=dev, dtype=torch.float64) + 0.5)/sq
+            y1 = (torch.arange(nyp*sq, device=dev, dtype=torch.float64) + 0.5)/sq
+            # np.meshgrid(x1, y1) flattened: x runs fastest
+            d[0, :N] = x1.repeat(nyp*sq)
+            d[1, :N] = y1.repeat_interleave(nx*sq) + manifold.edges[0]
+        else:
+            d[0, :N] = torch.rand(N, **kw)*nx
+            d[1, :N] = torch.rand(N, **kw)*nyp + manifold.edges[0]
         d[2:5, :N] = torch.randn((3, N), **kw)*self.vt
         ions.N = N
         ions._sorted = False
@@ -100,10 +116,31 @@ class DensityPertubation(InitialCondition):
         kx = self.ikx*2*np.pi/manifold.Lx
         ky = self.iky*2*np.pi/manifold.Ly
         N = ions.N
+        A = self.ampl
+        self.f = lambda x, y: 1 + A*np.cos(kx*x + ky*y)
+        if self.on_device:
+            # the same Newton iteration on the device tensors (no host copy of the
+            # particles: this is what makes a 1e9-particle perturbed start possible)
+            import torch
+            ions._dense()
+            d = ions._data
+            u = d[0, :N]/manifold.nx
+            y = y0 + d[1, :N]*manifold.dy
+            s0 = torch.sin(kx*x0 + ky*y)
+            X = x0 + u*Lx
+            for it in range(50):
+                ph = kx*X + ky*y
+                f = ((X - x0) + A/kx*(torch.sin(ph) - s0))/Lx - u
+                dX = f/((1 + A*torch.cos(ph))/Lx)
+                X = X - dX
+                if float(dX.abs().max()) < 1e-15*Lx:
+                    break
+            d[0, :N] = (X - x0)/manifold.dx
+            ions._touched()
+            return
         # x-coordinate in units of the box size, y in "physical" units
         u = np.asarray(ions['x'])[:N]/manifold.nx
         y = y0 + np.asarray(ions['y'])[:N]*manifold.dy
-        A = self.ampl
         s0 = np.sin(kx*x0 + ky*y)
         X = x0 + u*Lx                       # exact for ampl = 0
         for it in range(50):
@@ -112,6 +149,5 @@ class DensityPertubation(InitialCondition):
             X = X - dX
             if np.abs(dX).max() < 1e-15*Lx:
                 break
-        self.f = lambda x, y: 1 + A*np.cos(kx*x + ky*y)
         ions['x'][:N] = (X - x0)/manifold.dx
         ions['y'][:N] = (y - y0)/manifold.dy

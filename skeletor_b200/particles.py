@@ -70,6 +70,21 @@ class ParticleSlice:
         return len(self)
 
 
+class ParticleRow(DeviceArray):
+    """ions['x'] — a LIVE view of one coordinate row, like the reference's NumPy field
+    view: the tensor is looked up on every access, so a proxy kept across push / sort /
+    layout changes (all of which swap the underlying buffers) never goes stale."""
+
+    def __init__(self, parent, row):
+        self._parent, self._row = parent, row
+        self._on_write = parent._touched
+
+    @property
+    def t(self):
+        self._parent._dense()
+        return self._parent._data[self._row]
+
+
 class Particles:
     """Container class for particles in a given subdomain"""
 
@@ -235,7 +250,7 @@ class Particles:
     def __getitem__(self, key):
         self._dense()
         if isinstance(key, str):
-            return DeviceArray(self._data[_ROW[key]], on_write=self._touched)
+            return ParticleRow(self, _ROW[key])
         if isinstance(key, slice):
             return ParticleSlice(self, key)
         return np.asarray(ParticleSlice(self, slice(None)))[key]

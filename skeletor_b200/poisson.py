@@ -3,9 +3,10 @@ PoissonSolver in manifolds/second_order.py:101-213, grad_inv_del / calc_form_fac
 in cython/operators.pyx:13-135 and ppic2's cwppfft2r / cwppfft2r2).
 
 cuFFT (through torch.fft) replaces ppic2's hand-rolled radix-2 FFT and MPI transposes;
-the k-space multiply is a handful of elementwise ops on the [ny][nx/2+1] spectrum.
-With more than one rank the (small) electrostatic grids are gathered and every rank
-solves the full problem redundantly, keeping its own slab.
+the k-space part (form factors, -i k / k^2 multiply, field energy) is one kernel,
+skb_poisson_kspace, on the [ny][nx/2+1] spectrum.  With more than one rank the (small)
+electrostatic grids are all-gathered on the device (NCCL) and every rank solves the full
+problem redundantly, keeping its own slab.
 
 Reference quirk Q3: operators.pyx evaluates the form factors
 and the charge spectrum through crealf/cimagf, i.e. truncated to float32, so the
@@ -14,6 +15,9 @@ the truncation; parity with the reference is therefore at the 1e-6 level, not 1e
 """
 import numpy as np
 import torch
+
+from . import _lib
+from .field import _stream
 
 
 class PoissonSolver:
@@ -28,64 +32,36 @@ class PoissonSolver:
         self.indy = int(np.log2(grid.ny))
         assert grid.nx == 2**self.indx, "'nx' needs to be a power of two"
         assert grid.ny == 2**self.indy, "'ny' needs to be a power of two"
-        self._factors = None
-
-    def _build(self, device):
-        g = self.grid
-        nx, ny = g.nx, g.ny
-        nxh, nyh = nx//2, max(1, ny//2)
-        j = np.arange(nxh + 1)
-        k = np.arange(ny)
-        ks = np.where(k <= ny//2, k, k - ny)
-        dkx = 2.0*np.pi/g.Lx*j                  # operators.pyx:32-33, 39
-        dky = 2.0*np.pi/g.Ly*ks
-        KX, KY = np.meshgrid(dkx, dky)          # [ny][nxh+1]
-        at3 = KY*KY + KX*KX
-        at4 = np.exp(-.5*((KY*self.ay)**2 + (KX*self.ax)**2))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            re = np.where(at3 == 0.0, self.affp, self.affp*at4/at3)   # :46-49
-        im = np.where(at3 == 0.0, 1.0, at4)
-        if self.float32_quirk:
-            at1 = (re.astype(np.float32)*im.astype(np.float32)).astype(np.float64)
-        else:
-            at1 = re*im
-        # modes the reference zeroes: kx = 0 & ky = 0, kx = nx/2, ky = ny/2
-        keep = np.ones_like(at1)
-        keep[:, nxh] = 0.0
-        if ny > 1:
-            keep[nyh, :] = 0.0
-        keep[0, 0] = 0.0
-        at1 = at1*keep
-        t = lambda a: torch.as_tensor(a, device=device)
-        self._factors = (t(at1*KX), t(at1*KY))
+        self._buf = None
 
     def __call__(self, rho, E):
-        """E = grad del^-2 rho on the active cells; E.z = 0 (second_order.py:165-213)"""
+        """E = grad del^-2 rho on the active cells; E.z = 0 (second_order.py:165-213).
+        Returns (ttp, we) like the reference: transform time (not measured here: 0.0)
+        and the field energy of grad_inv_del (operators.pyx:135)."""
         g = self.grid
         comm = g.comm
         act = rho._active_t().contiguous()
-        if comm.size > 1:
-            parts = comm.allgather(act.cpu().numpy())
-            full = torch.as_tensor(np.concatenate(parts), device=act.device)
-        else:
-            full = act
-        if self._factors is None:
-            self._build(full.device)
-        fx, fy = self._factors
-        q = torch.fft.rfft2(full)
-        if self.float32_quirk:
-            q = torch.complex(q.real.float().double(), q.imag.float().double())
-        # -i k S(k)/k^2 rho_k  (operators.pyx:88-118)
-        mi = torch.complex(q.imag, -q.real)
-        ex = torch.fft.irfft2(fx*mi, s=full.shape)
-        ey = torch.fft.irfft2(fy*mi, s=full.shape)
+        # the (small) electrostatic grid is gathered on the device (NCCL all-gather) and
+        # every rank solves the full problem, keeping its own slab
+        full = comm.allgather_tensor(act) if comm.size > 1 else act
+        q = torch.fft.rfft2(full)                 # cuFFT R2C, [ny][nx/2+1] complex128
+        if self._buf is None or self._buf[0].shape != q.shape:
+            self._buf = (torch.empty_like(q), torch.empty_like(q),
+                         torch.zeros(1, dtype=torch.float64, device=q.device))
+        fx, fy, we = self._buf
+        we.zero_()
+        _lib.call("skb_poisson_kspace", q.data_ptr(), fx.data_ptr(), fy.data_ptr(), g.nx,
+                  g.ny, float(g.Lx), float(g.Ly), float(self.ax), float(self.ay),
+                  float(self.affp), int(bool(self.float32_quirk)), we.data_ptr(), _stream())
+        ex = torch.fft.irfft2(fx, s=full.shape)
+        ey = torch.fft.irfft2(fy, s=full.shape)
         sl = slice(g.noff, g.noff + g.nyp)
         Et = E.t[g.lby:g.uby, g.lbx:g.ubx]
         Et[..., 0] = ex[sl]
         Et[..., 1] = ey[sl]
         Et[..., 2] = 0.0
         E.boundaries_set = False
-        return 0.0, None
+        return 0.0, float(we.item())
 
 
 class Poisson:

@@ -36,6 +36,14 @@ def _worker(rank, size, port, q):
         fb, fa = world.ring_exchange(up, dn)
         below, above = (rank - 1) % size, (rank + 1) % size
         assert torch.all(fb == 10*below + 1) and torch.all(fa == 10*above + 2)
+        # device-tensor collectives of the steppers / Poisson solve (host tensors here)
+        acc = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        world.allreduce_tensor_(acc)
+        assert float(acc) == size*(size + 1)/2
+        slab = torch.full((3, 4), float(rank), dtype=torch.float64)
+        full = world.allgather_tensor(slab)
+        assert full.shape == (3*size, 4)
+        assert all(torch.all(full[3*r:3*r + 3] == r) for r in range(size))
         # object sendrecv (mpi4py lowercase API)
         got = world.sendrecv(np.arange(4.0) + rank, dest=above, source=below)
         assert np.array_equal(got, np.arange(4.0) + below)

@@ -70,8 +70,13 @@ def test_scenario_matches_reference(name, layout, capsys):
     assert set(res) == set(gold.files)
     if layout == "gapped":
         assert GAPPED_PUSHES[0] > 0, "the gapped push never ran"
-    # the steppers iterate Ohm/Faraday to convergence and amplify rounding a bit
-    rtol = 1e-10 if ("horowitz" in name or "predictor" in name) else 1e-12
+    # north star: <= 1e-12 relative.  The steppers iterate Ohm / Faraday (log(rho), a
+    # division by rho, a convergence loop) and amplify the last-bit differences of the
+    # deposit a little: measured against the single-rank golden fixtures E 6.6e-13
+    # (horowitz_cic) and 2.5e-13 (predictor_corrector_tsc), B 4.4e-16, particles 2e-16
+    # (profiles/mgpu_check_r02_*.log), i.e. inside the bound with a factor of two to
+    # spare for other summation orders
+    rtol = 2e-12 if ("horowitz" in name or "predictor" in name) else 1e-12
     if name == "poisson":
         # the reference truncates the spectrum to float32 (operators.pyx:6-8, 97-101;
         # SURVEY.md Q3): parity is defined at that level
@@ -200,3 +205,79 @@ def test_piecewise_guard_api_equals_fused():
     assert np.all(np.asarray(a) == np.asarray(b)) and np.all(np.asarray(a) == np.asarray(c))
     a += b
     assert np.allclose(np.asarray(a['t']), 2*np.asarray(b['t']))
+
+
+def test_particle_proxies_stay_live_across_pushes():
+    """the reference returns NumPy views: `vx = ions['vx']` stays valid for the whole run
+    (a proxy bound to one buffer went stale when push / sort swapped buffers)"""
+    import skeletor_b200 as sk
+    m = sk.Manifold(32, 32, sk.COMM_SELF)
+    n = 32*32*8
+    ions = sk.Particles(m, 4*n)
+    x, y, vx, vy, vz = sc.maxwellian(32, 32, 8, 0.5, 5)
+    ions.initialize(x, y, vx, vy, vz)
+    E = sk.Field(m, dtype=sk.Float3); E.copy_guards()
+    B = sk.Field(m, dtype=sk.Float3); B.copy_guards()
+    px, pvx = ions['x'], ions['vx']
+    for it in range(3):
+        ions.push(E, B, 0.3*m.dx)
+    now = np.asarray(ions[:ions.N])
+    assert np.array_equal(np.asarray(px)[:ions.N], now['x'])
+    pvx[:ions.N] = 0.25                      # a write through the old proxy lands
+    assert np.all(np.asarray(ions[:ions.N])['vx'] == 0.25)
+
+
+def test_kick_is_push_without_drift():
+    """Particles.kick (north star): velocities bit-identical to the oracle's push,
+    positions, time and count untouched"""
+    import skeletor_b200 as sk
+    from oracle import oracle as orc
+    nx, ny, npc = 32, 16, 8
+    n = nx*ny*npc
+    x, y, vx, vy, vz = sc.maxwellian(nx, ny, npc, 0.3, 9)
+    for order in (1, 2):
+        m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
+        g = orc.Grid(nx, ny, lbx=2, lby=2)
+        E = sc.smooth_field(sk, m, 0.2, "E")
+        B = sc.smooth_field(sk, m, 1.0, "B")
+        dt = 0.2*m.dx
+        ions = sk.Particles(m, 4*n, charge=0.7, mass=1.3, order=order)
+        ions.initialize(x, y, vx, vy, vz)
+        p = np.zeros(n, orc.Particle)
+        p["x"], p["y"] = x/g.dx, y/g.dy
+        p["vx"], p["vy"], p["vz"] = vx, vy, vz
+        exp = p.copy()
+        orc.push(exp, np.asarray(E).copy(), np.asarray(B).copy(), g, order, 0.7/1.3*dt/2, dt)
+        exp["x"], exp["y"] = p["x"], p["y"]          # kick: no drift
+        ions.kick(E, B, dt)
+        assert ions.time == 0.0 and ions.N == n
+        assert np.array_equal(rows(np.asarray(ions[:n])), rows(exp)), order
+
+
+def test_on_device_quiet_start_and_density_perturbation():
+    """initial_condition.py:20-62, 65-143 generated in device memory: the quiet start's
+    sub-lattice is bit-identical to the host path, the perturbed positions agree to
+    rounding of sin / cos (1e-13 cells)"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 32, 16, 16
+    m = sk.Manifold(nx, ny, sk.COMM_SELF)
+    n = nx*ny*npc
+    host = sk.Particles(m, 2*n)
+    dev = sk.Particles(m, 2*n)
+    np.random.seed(3)
+    sk.InitialCondition(npc, quiet=True, vt=0.0)(m, host)
+    sk.InitialCondition(npc, quiet=True, vt=0.0, on_device=True)(m, dev)
+    assert host.N == dev.N == n
+    a, b = np.asarray(host[:n]), np.asarray(dev[:n])
+    assert np.array_equal(a['x'], b['x']) and np.array_equal(a['y'], b['y'])
+    host2 = sk.Particles(m, 2*n)
+    dev2 = sk.Particles(m, 2*n)
+    sk.DensityPertubation(npc, 1, 0, 0.2, quiet=True, vt=0.0)(m, host2)
+    sk.DensityPertubation(npc, 1, 0, 0.2, quiet=True, vt=0.0, on_device=True)(m, dev2)
+    a, b = np.asarray(host2[:n]), np.asarray(dev2[:n])
+    assert np.abs(a['x'] - b['x']).max() < 1e-12 and np.array_equal(a['y'], b['y'])
+    src = sk.Sources(m)
+    src.deposit(dev2, set_boundaries=True)
+    rho = src.rho.trim()
+    xg, yg = np.meshgrid(m.x, m.y)
+    assert np.abs(rho - (1 + 0.2*np.cos(2*np.pi*xg/m.Lx))).max() < 0.02

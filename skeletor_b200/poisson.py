@@ -44,9 +44,12 @@ class PoissonSolver:
         # the (small) electrostatic grid is gathered on the device (NCCL all-gather) and
         # every rank solves the full problem, keeping its own slab
         full = comm.allgather_tensor(act) if comm.size > 1 else act
-        q = torch.fft.rfft2(full)                 # cuFFT R2C, [ny][nx/2+1] complex128
+        # cuFFT R2C, [ny][nx/2+1] complex128 (torch hands the 2-D transform back with
+        # transposed strides: the kernel wants the plain row-major spectrum)
+        q = torch.fft.rfft2(full).contiguous()
         if self._buf is None or self._buf[0].shape != q.shape:
-            self._buf = (torch.empty_like(q), torch.empty_like(q),
+            self._buf = (torch.empty(q.shape, dtype=q.dtype, device=q.device),
+                         torch.empty(q.shape, dtype=q.dtype, device=q.device),
                          torch.zeros(1, dtype=torch.float64, device=q.device))
         fx, fy, we = self._buf
         we.zero_()

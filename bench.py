@@ -58,7 +58,7 @@ def parse():
                     help="5 %% sinusoidal density contrast along x (SURVEY.md 8d)")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling: ny grows with the GPU count (ny rows PER GPU)")
-    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5],
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5],
                     help="BASELINE.json config: 5 (default, the one the metric is quoted on) "
                          "uniform plasma push+deposit; 2 Landau loop incl. Ohm, 1024^2 x 64 "
                          "ppc; 3 Horowitz iterate, 2048^2 x 128 ppc, Hall Ohm + Faraday; 4 "
@@ -350,6 +350,8 @@ def b200_arm(a):
     n_total = a.nx*a.ny*a.ppc
     gapped = a.layout == "gapped"
     nmax = int((1.36 if gapped else 1.05)*n_local) + 4096
+    if gapped:          # + 4 slots for every empty cell of the tiles covering the grid
+        nmax += 4*256*((m.mx + 15)//16)*((m.myp + 15)//16)
     nmax += nmax & 1
     ions = sk.Particles(m, nmax, charge=1.0, mass=1.0, order=a.order,
                         nbmax=max(n_local//100, 1 << 16))
@@ -703,6 +705,10 @@ def b200_arm(a):
 
 # ----------------------------------------------------------------------------------
 CONFIGS = {
+    1: dict(nx=32, ny=32, ppc=256, what="ion-acoustic wave test at its default small grid "
+            "(BASELINE config 1, reference tests/test_ionacoustic.py:160-178: 45 steps per "
+            "wave period): push + deposit + add_guards + copy_guards + Ohm + copy_guards "
+            "per step; launch / synchronisation bound at this size"),
     2: dict(nx=1024, ny=1024, ppc=64, what="Landau / ion-acoustic loop (BASELINE config 2): "
             "push + deposit + add_guards + copy_guards + Ohm + copy_guards per step"),
     3: dict(nx=2048, ny=2048, ppc=121, what="hybrid stepper (BASELINE config 3): one Horowitz "
@@ -731,7 +737,7 @@ def config_arm(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    lb = 1 if a.config == 2 else 2
+    lb = 1 if a.config in (1, 2) else 2
     if a.config == 4:
         m = sk.ShearingManifold(a.nx, a.ny, comm, lbx=lb, lby=lb, S=-1.5, Omega=1.0,
                                 Lx=1.0, Ly=a.ny/a.nx)
@@ -741,7 +747,9 @@ def config_arm(a):
         m = sk.Manifold(a.nx, a.ny, comm, lbx=lb, lby=lb, Lx=1.0, Ly=a.ny/a.nx)
     n_local = a.nx*m.nyp*a.ppc
     n_total = a.nx*a.ny*a.ppc
-    nmax = int(1.36*n_local) + 4096
+    # slot ranges of the gapped layout: 25 % slack per cell + 4 slots for every empty cell
+    # of the 16 x 16 tiles that cover the extended grid
+    nmax = int(1.36*n_local) + 4096 + 4*256*((m.mx + 15)//16)*((m.myp + 15)//16)
     nmax += nmax & 1
     ions = sk.Particles(m, nmax, charge=1.0, mass=1.0, order=1,
                         nbmax=max(n_local//100, 1 << 16))
@@ -774,7 +782,7 @@ def config_arm(a):
     hot = ["skb_push_gapped", "skb_boris_push", "skb_deposit", "skb_push_and_deposit_gapped",
            "skb_push_and_deposit"]
     stepper = None
-    if a.config == 2:
+    if a.config in (1, 2):
         dt = 0.1*m.dx
         E.copy_guards(); B.copy_guards()
         ohm = sk.Ohm(m, temperature=1.0, charge=1.0)
@@ -877,7 +885,7 @@ def config_arm(a):
                 "others": {k: v for k, v in kern.items() if k != dom}}
     layout = ions._rep
     checks = {}
-    if a.config in (2, 4) and not a.no_parity:
+    if a.config in (1, 2, 4) and not a.no_parity:
         checks.update(parity_checks(sk, ions, E, B, src, dt, comm, a,
                                     modified=a.config == 4))
     n_now = comm.allreduce(int(ions.N), op=sk.comm.SUM) if size > 1 else int(ions.N)
@@ -894,6 +902,10 @@ def config_arm(a):
                            "l2_policy": "inputs larger than L2"},
                 "roofline": roofline, "kernels": kern, "cpu_baseline": None, "e2e": None,
                 "gpu_launches": launches, "clocks": clk, "checks": checks, "impl": "b200"}
+        if a.config == 1:
+            # the reference's whole test file (import + 45 steps, quiet start) takes 22.5 s
+            # single-rank on the survey's CPU
+            line["config"]["seconds_per_45_steps"] = 45*ms/a.steps*1e-3
         print(json.dumps(line), flush=True)
 
 

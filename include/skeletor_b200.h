@@ -78,6 +78,7 @@ typedef struct {
 #define SKB_EPI_HOLES 4      /* calculate_ihole (unordered list + count)      */
 #define SKB_EPI_COUNT 8      /* histogram of the NEW cell keys of the particles that
                                 stay in the slab (first pass of the tile sort, fused) */
+#define SKB_EPI_DRIFT_ONLY 16 /* (gapped sweeps) no gather / kick: drift, particle_push.pyx:159-169 */
 
 typedef struct {
   int flags;
@@ -331,6 +332,14 @@ int skb_push_deposit_gapped(skb_particles_t p, const double *E, const double *B,
 /* deposit_cic/tsc (deposit.pyx:6,21) of n AoS rows {x, y, vx, vy, vz} into `current` */
 int skb_deposit_rows(const double *rows, int n, double *current, const skb_grid_t *grid,
                      int order, double S, void *stream);
+/* drift (particle_push.pyx:159-169) + periodic_x + the routing of skb_push_gapped on the
+ * gapped layout: Particles.drift (particles.py:259-265) without leaving the layout. */
+int skb_drift_gapped(skb_particles_t p, const skb_grid_t *grid, int order, double dt,
+                     int tlx, int tly, const int *gap_start, int *gap_count, double *movers,
+                     int mover_cap, double *sbufl, double *sbufr, int nbmax, int *counts,
+                     int rank, int nvp, double *leftover, int leftover_cap, int nleft,
+                     int *leftover_counts, double *scratch, int scratch_rows, int npool,
+                     int *pool_owner, void *stream);
 int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
                    int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
                    double *leftover, int leftover_cap, int *counts, void *stream);

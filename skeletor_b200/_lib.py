@@ -91,6 +91,9 @@ SIGNATURES = {
                                 c_int, c_dbl, c_dbl, c_vp, c_dbl, c_int, c_int, c_vp, c_vp,
                                 c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp,
                                 c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
+    "skb_drift_gapped": [_P, _G, c_int, c_dbl, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp,
+                         c_int, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int,
+                         c_int, c_vp, c_vp],
     "skb_deposit_rows": [c_vp, c_int, c_vp, _G, c_int, c_dbl, c_vp],
     "skb_gap_insert": [c_vp, c_int, _P, c_vp, c_vp, _G, c_int, c_int, c_int, c_vp, c_int,
                        c_vp, c_vp],

@@ -442,7 +442,8 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
     ixe[p] = (int)xe[p]; iye[p] = (int)ye[p]; ixb[p] = (int)xb[p]; iyb[p] = (int)yb[p];
     ok = ok && ixe[p] == c.cix && iye[p] == c.ciy;
   }
-  if (CS_ABLATE & 4) {
+  if ((CS_ABLATE & 4) || (q.flags & SKB_EPI_DRIFT_ONLY)) {
+    // drift alone (particle_push.pyx:159-169): velocities stay as they are
   } else if (c.fast && __all_sync(SKB_FULL, ok)) {
 #pragma unroll
     for (int p = 0; p < NP; p++) {
@@ -670,8 +671,10 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (PD != 0) zero_window(sS, CS_WIN4);
-  stage_window(sE, E, w, CS_WS, g);
-  stage_window(sB, B, w, CS_WS, g);
+  if (!(q.flags & SKB_EPI_DRIFT_ONLY)) {
+    stage_window(sE, E, w, CS_WS, g);
+    stage_window(sB, B, w, CS_WS, g);
+  }
   __syncthreads();
   double *const scr = s_blk >= 0 ? q.scratch + (size_t)s_blk * q.scratch_rows * 5 : nullptr;
   const int scr_rows = s_blk >= 0 ? (q.scratch_rows & ~31) : 0;    // whole halves only

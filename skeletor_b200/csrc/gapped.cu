@@ -574,7 +574,8 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
   // tiles; SKB_GAP_GENERIC=1 keeps the generic kernel below (A/B measurements)
   static const bool force_generic = getenv("SKB_GAP_GENERIC") && atoi(getenv("SKB_GAP_GENERIC"));
   const bool stream_kernel = (pd == 0 || pd == 3) && tlx == 4 && tly == 4 && !force_generic;
-  if (pd == 3 && !stream_kernel) return (int)cudaErrorNotSupported;
+  if ((pd == 3 || (epi_flags & SKB_EPI_DRIFT_ONLY)) && !stream_kernel)
+    return (int)cudaErrorNotSupported;
   cudaError_t e = cudaMemsetAsync(counts, 0, 5 * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (q.npool > 0) {       // (all blocks free: a failed earlier launch cannot leave claims)
@@ -649,8 +650,11 @@ static int gapped_sweep(int pd, skb_particles_t p, const double *E, const double
       skb_epilogue_t ep = {};
       ep.flags = epi_flags & (SKB_EPI_SHEAR | SKB_EPI_PERIODIC_X);
       ep.S = epi_S; ep.t = epi_t;
-      rc = skb_boris_push(lp, nleft, E, B, grid, order, qtmh, dt, modified, Omega, S, nullptr,
-                          &ep, stream);
+      if (epi_flags & SKB_EPI_DRIFT_ONLY)
+        rc = skb_drift(lp, nleft, dt, grid, &ep, stream);
+      else
+        rc = skb_boris_push(lp, nleft, E, B, grid, order, qtmh, dt, modified, Omega, S,
+                            nullptr, &ep, stream);
     }
     if (rc) return rc;
     if (pd != 2) {
@@ -747,4 +751,19 @@ extern "C" int skb_deposit_rows(const double *rows, int n, double *current,
     gap_deposit_rows_kernel<2><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, n, current, dp, g);
   SKB_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int skb_drift_gapped(skb_particles_t p, const skb_grid_t *grid, int order, double dt,
+                                int tlx, int tly, const int *gap_start, int *gap_count,
+                                double *movers, int mover_cap, double *sbufl, double *sbufr,
+                                int nbmax, int *counts, int rank, int nvp, double *leftover,
+                                int leftover_cap, int nleft, int *leftover_counts,
+                                double *scratch, int scratch_rows, int npool, int *pool_owner,
+                                void *stream) {
+  // (E, B are never read with SKB_EPI_DRIFT_ONLY)
+  return gapped_sweep(0, p, nullptr, nullptr, grid, order, 0.0, dt, 0, 0.0, 0.0,
+                      SKB_EPI_PERIODIC_X | SKB_EPI_DRIFT_ONLY, 0.0, 0.0, nullptr, 0.0, nullptr, 0,
+                      tlx, tly, gap_start, gap_count, movers, mover_cap, sbufl, sbufr, nbmax,
+                      counts, rank, nvp, leftover, leftover_cap, nleft, leftover_counts, scratch,
+                      scratch_rows, npool, pool_owner, stream);
 }

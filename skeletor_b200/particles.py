@@ -932,9 +932,26 @@ class Particles:
 
     def drift(self, dt):
         """particles.py:259-265: drift, then periodic_x and periodic_y"""
-        self._dense()
         self._fused_valid = False
         self._last_op = None
+        if self.gapped and self.order in (1, 2) and \
+                (self._rep == "gapped" or self._to_gapped()):
+            # on the gapped layout: the cell-stream sweep without gather / kick
+            m = self.manifold
+            comm = m.comm
+            cnt = self._counts
+            _lib.call("skb_drift_gapped", self._c, m.c, self.order, float(dt), TLX, TLY,
+                      self._gap_start.data_ptr(), self._gap_count.data_ptr(),
+                      self._movers.data_ptr(), self._movers.shape[0],
+                      self.sbufl.data_ptr(), self.sbufr.data_ptr(), self.nbmax,
+                      cnt.data_ptr(), comm.rank, comm.size, self._leftover.data_ptr(),
+                      self._leftover.shape[1], self._gap_nleft, self._gcnt.data_ptr(),
+                      self._scratch.data_ptr(), self._scr_rows, self._npool,
+                      self._pool_owner.data_ptr(), _stream())
+            self._gap_finish(cnt)
+            self._gap_pushes += 1
+            return
+        self._dense()
         flags = _lib.EPI_HOLES | _lib.EPI_PERIODIC_X
         _lib.call("skb_drift", self._c, self.N, float(dt), self.manifold.c,
                   self._epilogue(flags), _stream())

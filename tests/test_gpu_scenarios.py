@@ -281,3 +281,32 @@ def test_on_device_quiet_start_and_density_perturbation():
     rho = src.rho.trim()
     xg, yg = np.meshgrid(m.x, m.y)
     assert np.abs(rho - (1 + 0.2*np.cos(2*np.pi*xg/m.Lx))).max() < 0.02
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_drift_on_gapped_layout_equals_oracle(order):
+    """Particles.drift (particles.py:259-265) without leaving the gapped layout
+    (skb_drift_gapped): bit-exact against the oracle's drift + cppmove2 + periodic_x"""
+    import skeletor_b200 as sk
+    from oracle import oracle as orc
+    nx, ny, npc = 64, 32, 16
+    n = nx*ny*npc
+    m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
+    g = orc.Grid(nx, ny, lbx=2, lby=2)
+    x, y, vx, vy, vz = sc.maxwellian(nx, ny, npc, 0.8, 21)
+    ions = sk.Particles(m, 4*n + 8192, order=order)
+    ions.gapped = True
+    ions.initialize(x, y, vx, vy, vz)
+    p = np.zeros(2*n, orc.Particle)
+    p["x"][:n], p["y"][:n] = x/g.dx, y/g.dy
+    p["vx"][:n], p["vy"][:n], p["vz"][:n] = vx, vy, vz
+    parts, N = [p], [n]
+    dt = 0.4*m.dx
+    for it in range(3):
+        ions.drift(dt)
+        assert ions._rep == "gapped"
+        orc.drift(parts[0][:N[0]], g, dt)
+        orc.periodic_x(parts[0][:N[0]], g)
+        parts, N = orc.move(parts, N, [g])
+        assert ions.N == N[0]
+    assert np.array_equal(rows(np.asarray(ions[:ions.N])), rows(parts[0][:N[0]]))

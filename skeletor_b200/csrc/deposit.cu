@@ -17,6 +17,7 @@
 // the window (stale ordering, unsorted tail) go to HBM directly.  Per-particle
 // weights are formed exactly as the reference does (ty*tx, then *vx, ...), so the
 // only difference to the reference is the order of the summation.
+#include <cstdlib>
 #include "deposit.cuh"
 
 
@@ -249,6 +250,84 @@ deposit_cells_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, Dev
     __syncthreads();
     flush_window(sw, w, wstride, cur, g);
   }
+}
+
+// Cell-aligned deposit for FEW particles per cell (CIC): every half-warp takes a cell of
+// its own, so one reduce-scatter (four exchange stages inside the half-warps) and one
+// emit serve TWO cells and all 32 lanes end up holding one of the 2 x 16 sums.  At 64
+// particles per cell the per-cell reduction + emit of deposit_cells_kernel is as much
+// work as the accumulation itself; here it is halved.
+__global__ void __launch_bounds__(DEP_THREADS, 2)
+deposit_cells_half_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
+                          DepParams q, int parts, int wstride, int wrows) {
+  constexpr int NS = 2, UNR = 4;
+  extern __shared__ double sw[];
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;          // cells per CTA
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const bool gapped = tl.gap_start != nullptr;
+  const int pbeg = gapped ? tl.gap_start[c0] : (c0 ? tl.cell_end[c0 - 1] : 0);
+  const int pend = gapped ? tl.gap_start[c0 + cpp] : tl.cell_end[c0 + cpp - 1];
+  if (pbeg == pend) return;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
+  const Window w = tile_window(tile, tl, g);
+  zero_window(sw, wstride * wrows * 4);
+  __syncthreads();
+  const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
+  const int cpw = cpp / (DEP_THREADS / 32);           // cells per warp (>= 1)
+  const int wc0 = c0 + wv * cpw;
+  for (int j = 0; j < cpw; j += 2) {
+    // my half's cell: [s, e)
+    const int jc = j + half;
+    int s = 0, e = 0;
+    if (jc < cpw) {
+      const int cell = wc0 + jc;
+      if (gapped) { s = tl.gap_start[cell]; e = s + tl.gap_count[cell]; }
+      else { s = cell ? tl.cell_end[cell - 1] : 0; e = tl.cell_end[cell]; }
+    }
+    const int n = e - s;
+    const int nmax = max(n, __shfl_xor_sync(SKB_FULL, n, 16));
+    if (nmax == 0) continue;
+    const int local = (wc0 + min(jc, cpw - 1)) & ((1 << cells_log2) - 1);
+    Acc<NS> a;
+#pragma unroll
+    for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+    a.ix = bx + (local & ((1 << tl.tlx) - 1));
+    a.iy = by + (local >> tl.tlx);
+    for (int base = 0; base < nmax; base += 16 * UNR) {
+      double x[UNR], y[UNR], vx[UNR], vy[UNR], vz[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const int k = base + u * 16 + hl;
+        if (k < n) {
+          const int i = s + k;
+          x[u] = P.x[i]; y[u] = P.y[i]; vx[u] = P.vx[i]; vy[u] = P.vy[i]; vz[u] = P.vz[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const int k = base + u * 16 + hl;
+        if (k < n) {
+          const double xs = x[u] + q.offx, ys = y[u] + q.offy;
+          int ix, iy;
+          double wx[NS], wy[NS];
+          particle_terms<1>(xs, ys, ix, iy, wx, wy);
+          const double vxr = vx[u] + q.S * (y[u] * g.dy + g.y0);      // deposit.pxd:24
+          if (ix == a.ix && iy == a.iy) accumulate<1>(a, wx, wy, vxr, vy[u], vz[u]);
+          else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy[u], vz[u], cur, g);
+        }
+      }
+    }
+    const bool in_window = (a.ix >= w.x0) && (a.ix + NS <= w.x1) && (a.iy >= w.y0) &&
+                           (a.iy + NS <= w.y1);
+    warp_reduce_scatter<16, true>(a.v, lane);
+    if (n > 0)
+      emit_one<NS>(a.v[0], scatter_index<16>(hl), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+  }
+  __syncthreads();
+  flush_window(sw, w, wstride, cur, g);
 }
 
 // Deterministic second phase: every grid cell adds the contributions of the (up to
@@ -502,7 +581,13 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
       SKB_CHECK_LAUNCH();
       return 0;
     }
-    if (order == 1)
+    // few particles per cell (CIC): two cells per warp (SKB_DEP_HALF=0/1 overrides)
+    static const int half_env = getenv("SKB_DEP_HALF") ? atoi(getenv("SKB_DEP_HALF")) : -1;
+    const double ppc = (double)np / ((double)g.nx * (double)g.nyp);
+    const bool half = half_env >= 0 ? half_env != 0 : ppc < 100.0;
+    if (order == 1 && half)
+      deposit_cells_half_kernel<<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
+    else if (order == 1)
       deposit_cells_kernel<1, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);
     else
       deposit_cells_kernel<2, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);

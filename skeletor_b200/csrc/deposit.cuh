@@ -202,7 +202,9 @@ __device__ __forceinline__ int scatter_index(int lane) {
   return idx;
 }
 
-template <int V>
+// HALF: the two half-warps reduce independently (V = 16 values over 16 lanes each): used
+// when every half-warp accumulates a cell of its own.
+template <int V, bool HALF = false>
 __device__ __forceinline__ void warp_reduce_scatter(double *v, int lane) {
   int bit = 1;
 #pragma unroll
@@ -217,7 +219,7 @@ __device__ __forceinline__ void warp_reduce_scatter(double *v, int lane) {
     }
   }
 #pragma unroll
-  for (; bit < 32; bit <<= 1) v[0] += __shfl_xor_sync(SKB_FULL, v[0], bit);
+  for (; bit < (HALF ? 16 : 32); bit <<= 1) v[0] += __shfl_xor_sync(SKB_FULL, v[0], bit);
 }
 
 // add value number idx (= (r*NS + c)*4 + k) of a cell's stencil sums to the window

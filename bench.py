@@ -635,7 +635,7 @@ def b200_arm(a):
     # full size (profiles/traffic_r02.json names the capture), scaled by the particles
     # this launch processed
     tr = os.path.join(ROOT, "profiles", "traffic_r02.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and a.order == 1:          # (the captures are of the CIC kernels)
         try:
             rec = json.load(open(tr)).get(dom)
             if rec:

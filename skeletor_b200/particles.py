@@ -195,6 +195,17 @@ class Particles:
         self._fused_used = False
         self._fused_S = 0.0
         self._last_op = None
+        # Multi-rank runs: push() returns once its kernel is queued; the migration that
+        # completes it (count read-back, neighbour exchange, classification: three host
+        # round trips) runs on a second stream and is only waited for when something needs
+        # the particles - Sources.deposit(ions) first deposits the cells the kernel left
+        # behind and lets the exchange overlap that sweep.  Errors of the migration
+        # (buffer overflows) then surface at that point instead of inside push().
+        ov = os.environ.get("SKELETOR_B200_OVERLAP")
+        self.overlap_migration = (manifold.comm.size > 1) if ov is None else ov == "1"
+        self._pending = None
+        self._side = None
+        self._cnt_host = None
         self._gap_fail = None         # N at which the slot ranges did not fit
         self._gap_thrash = 0          # gapped -> dense conversions after a single push
         self._gap_pushes = 0
@@ -208,6 +219,7 @@ class Particles:
     @property
     def N(self):
         """number of particles in this slab"""
+        self._finish_pending()
         return self._N
 
     @N.setter
@@ -227,6 +239,7 @@ class Particles:
         every normalize, sources.py:55-59; it only changes when N is assigned)"""
         if self._N_global is None:
             from .comm import SUM
+            self._finish_pending()
             self._N_global = self.manifold.comm.allreduce(int(self._N), op=SUM)
         return self._N_global
 
@@ -411,6 +424,7 @@ class Particles:
 
     def _dense(self):
         """back to the dense representation every other method works on"""
+        self._finish_pending()
         if self._rep != "gapped":
             return
         self._gap_thrash = self._gap_thrash + 1 if self._gap_pushes <= 1 else 0
@@ -447,9 +461,48 @@ class Particles:
             return False
         fuse = self.fuse_deposit is True or \
             (self.fuse_deposit == "auto" and self._fuse_next)
-        self._gap_finish(self._gap_kernel(E, B, dt, modified, fuse), fused=fuse)
+        cnt = self._gap_kernel(E, B, dt, modified, fuse)
+        if self.overlap_migration and not fuse:
+            self._start_pending(cnt)
+        else:
+            self._gap_finish(cnt, fused=fuse)
         self._gap_pushes += 1
         return True
+
+    # -- migration overlapped with the deposit (multi-rank) ------------------------------
+    def _start_pending(self, cnt):
+        """queue the read-back of the push kernel's counters on the side stream"""
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            self._cnt_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+            self._cnt_ev = torch.cuda.Event()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self._cnt_host[:5].copy_(cnt[:5], non_blocking=True)
+            self._cnt_host[5:7].copy_(self._gcnt[:2], non_blocking=True)
+            self._cnt_ev.record(self._side)
+        self._pending = cnt
+
+    def _finish_pending(self, deposit_into=None):
+        """complete the migration of the last push (no-op when nothing is pending).
+        deposit_into: a Sources whose grid already holds the deposit of the cells as the
+        push kernel left them; the rows that are inserted now are added to it."""
+        if getattr(self, "_pending", None) is None:
+            return
+        self._pending = None
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._side):
+            self._cnt_ev.synchronize()
+            nm, nl, nr, fl, nlocal, nleft_b, lost_b = self._cnt_host[:7].tolist()
+            self._gap_check_flags(fl)
+            nkeep = self._exchange(nl, nr)       # on the side stream: overlaps the deposit
+            done = torch.cuda.Event()
+            done.record(self._side)
+        main.wait_event(done)
+        self._gap_finish_tail(nm, nl, nr, fl, nlocal, nkeep, False, deposit_into, nleft_b)
 
     def _fused_sources(self):
         """private grid of the fused push + deposit sweep (raw sums, [myp][mx][4])"""
@@ -526,10 +579,7 @@ class Particles:
             msg = "ihole overflow error: ntmax={}, ierr={}"
             raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
 
-    def _gap_finish(self, cnt, cfl=False, fused=False):
-        m = self.manifold
-        st = _stream()
-        nm, nl, nr, fl, nlocal = cnt[:5].tolist()
+    def _gap_check_flags(self, fl, cfl=False):
         if cfl or (fl & 4):
             msg = "ihole overflow error: ntmax={}, ierr={}"
             raise RuntimeError(msg.format(self.ihole.numel() - 1, 1))
@@ -539,14 +589,37 @@ class Particles:
             raise RuntimeError("gapped layout: mover lists overflowed, particles were "
                                "lost (raise Particles.mover_fraction; {} rows)".format(
                                    self._movers.shape[0]))
+
+    def _gap_finish(self, cnt, cfl=False, fused=False):
+        nm, nl, nr, fl, nlocal = cnt[:5].tolist()
+        self._gap_check_flags(fl, cfl)
         nkeep = self._exchange(nl, nr)
+        self._gap_finish_tail(nm, nl, nr, fl, nlocal, nkeep, fused)
+
+    def _gap_finish_tail(self, nm, nl, nr, fl, nlocal, nkeep, fused, deposit_into=None,
+                         nleft_b=0):
+        m = self.manifold
+        st = _stream()
+        if deposit_into is not None:
+            # the cells were deposited as the push kernel left them: add what is inserted
+            # now (rows on the global mover list, arrivals) and the rows that kernel put
+            # on the leftover list itself
+            S = float(getattr(deposit_into.grid, 'S', 0.0))
+            for rows, n in ((self._movers, min(nm, self._movers.shape[0])),
+                            (self._keep, nkeep)):
+                _lib.call("skb_deposit_rows", rows.data_ptr(), n, deposit_into.ptr, m.c,
+                          self.order, S, st)
+            if nleft_b > 0:
+                _lib.call("skb_deposit", self._soa(self._leftover),
+                          min(nleft_b, self._leftover.shape[1]), deposit_into.ptr, m.c,
+                          self.order, S, None, st)
         if fused:
             # the arrivals were not in this slab when the push accumulated its grid
             _lib.call("skb_deposit_rows", self._keep.data_ptr(), nkeep,
                       self._fused_grid.data_ptr(), m.c, self.order, self._fused_S, st)
         self._fused_valid = fused and not (fl & 16)
         self._fused_used = False
-        new_n = self.N - nl - nr + nkeep
+        new_n = self._N - nl - nr + nkeep
         if new_n > self.size:
             self.info[0] = new_n - self.size
             raise RuntimeError("particle overflow error, ierr = {}".format(
@@ -749,6 +822,7 @@ class Particles:
         self.periodic_y()
 
     def _push(self, E, B, dt, modified):
+        self._finish_pending()
         if self._fused_valid and not self._fused_used:
             self._fuse_next = False        # the last fused deposit was not picked up
         self._fused_valid = False
@@ -889,6 +963,7 @@ class Particles:
         if self.order not in (1, 2):
             msg = 'Interpolation order {} not implemented.'
             raise RuntimeError(msg.format(self.order))
+        self._finish_pending()
         self._fused_valid = False
         self._last_op = None
         if self.gapped and self.gapped_push_and_deposit and \
@@ -932,6 +1007,7 @@ class Particles:
 
     def drift(self, dt):
         """particles.py:259-265: drift, then periodic_x and periodic_y"""
+        self._finish_pending()
         self._fused_valid = False
         self._last_op = None
         if self.gapped and self.order in (1, 2) and \

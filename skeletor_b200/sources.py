@@ -53,6 +53,19 @@ class Sources(Field):
             return
         if erase:
             self.t.zero_()
+        if getattr(particles, "_pending", None) is not None and \
+                particles._rep == "gapped" and not particles.deterministic:
+            # the push's migration is still in flight on the side stream: deposit the
+            # cells as the kernel left them while the neighbour exchange runs, then add
+            # the rows that are inserted when it completes (summation order only)
+            _lib.call("skb_deposit", particles._c, particles._N, self.ptr, self.grid.c,
+                      particles.order, float(S), particles._tiling_c(), _stream())
+            particles._finish_pending(deposit_into=self)
+            self.boundaries_set = False
+            self.normalize(particles)
+            if set_boundaries:
+                self.set_boundaries()
+            return
         if particles.deterministic:
             particles._dense()         # the fixed-order deposit needs the dense ordering
         particles._ensure_sorted()

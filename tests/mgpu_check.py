@@ -43,9 +43,13 @@ def main():
             super().__init__(manifold, 4*int(Nmax) + 8192, **kw)   # (empty cells own 4 slots each)
             self.gapped = True
 
-        def _gap_finish(self, cnt, *args, **kw):
+        def _gap_kernel(self, *args, **kw):
             pushes[0] += 1
-            return super()._gap_finish(cnt, *args, **kw)
+            return super()._gap_kernel(*args, **kw)
+
+        def _push_and_deposit_gapped(self, *args, **kw):
+            pushes[0] += 1
+            return super()._push_and_deposit_gapped(*args, **kw)
 
     ns = types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
@@ -61,8 +65,17 @@ def main():
     failed = 0
     for name in names:
         gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
-        with contextlib.redirect_stdout(io.StringIO()):
-            res = sc.SCENARIOS[name](ns)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = sc.SCENARIOS[name](ns)
+        except AssertionError as err:
+            if "slab too small" not in str(err):
+                raise
+            # the fixture's grid has fewer rows per rank than guard layers at this rank
+            # count (every rank hits the same assertion in Grid.__init__)
+            if comm.rank == 0:
+                print("%-26s ranks=%d SKIP  (%s)" % (name, comm.size, err), flush=True)
+            continue
         # gather the slabs on every rank (object allgather: diagnostics path)
         g = lb.get(name, 2)
         rtol = 2e-12 if ("horowitz" in name or "predictor" in name) else 1e-12

@@ -33,9 +33,13 @@ def namespace(gapped=False):
             super().__init__(manifold, 4*int(Nmax) + 8192, **kw)   # (empty cells own 4 slots each)
             self.gapped = True
 
-        def _gap_finish(self, cnt, *args, **kw):
+        def _gap_kernel(self, *args, **kw):
             GAPPED_PUSHES[0] += 1
-            return super()._gap_finish(cnt, *args, **kw)
+            return super()._gap_kernel(*args, **kw)
+
+        def _push_and_deposit_gapped(self, *args, **kw):
+            GAPPED_PUSHES[0] += 1
+            return super()._push_and_deposit_gapped(*args, **kw)
 
     return types.SimpleNamespace(
         Manifold=sk.Manifold, ShearingManifold=sk.ShearingManifold,
@@ -310,3 +314,36 @@ def test_drift_on_gapped_layout_equals_oracle(order):
         parts, N = orc.move(parts, N, [g])
         assert ions.N == N[0]
     assert np.array_equal(rows(np.asarray(ions[:ions.N])), rows(parts[0][:N[0]]))
+
+
+def test_overlapped_migration_equals_immediate():
+    """Particles.overlap_migration (default with more than one rank): push() returns with
+    its migration still in flight and Sources.deposit overlaps it - same particles (bit
+    for bit), same sources (summation order) as the immediate path"""
+    import skeletor_b200 as sk
+    nx, ny, npc = 64, 32, 16
+    n = nx*ny*npc
+    x, y, vx, vy, vz = sc.maxwellian(nx, ny, npc, 0.8, 31)
+    out = {}
+    for overlap in (False, True):
+        m = sk.Manifold(nx, ny, sk.COMM_SELF, lbx=2, lby=2)
+        E = sc.smooth_field(sk, m, 0.2, "E")
+        B = sc.smooth_field(sk, m, 1.0, "B")
+        ions = sk.Particles(m, 4*n + 8192)
+        ions.gapped = True
+        ions.overlap_migration = overlap
+        ions.initialize(x, y, vx, vy, vz)
+        src = sk.Sources(m)
+        for it in range(4):
+            ions.push(E, B, 0.4*m.dx)
+            assert (ions._pending is not None) == overlap
+            src.deposit(ions)
+            assert ions._pending is None
+            src.add_guards()
+            src.copy_guards()
+        ions.push(E, B, 0.4*m.dx)                 # finished by the read below
+        out[overlap] = (rows(np.asarray(ions[:ions.N])), np.asarray(src).view(np.float64).copy(),
+                        ions.N)
+    assert out[True][2] == out[False][2] == n
+    assert np.array_equal(out[True][0], out[False][0])
+    check("sources", out[True][1], out[False][1], 1e-12)

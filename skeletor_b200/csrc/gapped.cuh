@@ -15,7 +15,9 @@
 
 // One slot claim per warp and destination cell (rows arrive roughly ordered by source
 // tile, so a warp sees few distinct cells and its writes into one cell are contiguous).
+#ifndef GAP_INS_ITEMS
 #define GAP_INS_ITEMS 4
+#endif
 // Insert rows i0 + t*256 (t < GAP_INS_ITEMS, < n) into their cells; a warp-collective:
 // all 32 lanes of a warp call it together.  GAP_INS_ITEMS independent rows per thread:
 // the row load -> slot claim -> store chains overlap instead of adding up.

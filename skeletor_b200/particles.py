@@ -195,14 +195,15 @@ class Particles:
         self._fused_used = False
         self._fused_S = 0.0
         self._last_op = None
-        # Multi-rank runs: push() returns once its kernel is queued; the migration that
-        # completes it (count read-back, neighbour exchange, classification: three host
-        # round trips) runs on a second stream and is only waited for when something needs
-        # the particles - Sources.deposit(ions) first deposits the cells the kernel left
-        # behind and lets the exchange overlap that sweep.  Errors of the migration
-        # (buffer overflows) then surface at that point instead of inside push().
-        ov = os.environ.get("SKELETOR_B200_OVERLAP")
-        self.overlap_migration = (manifold.comm.size > 1) if ov is None else ov == "1"
+        # overlap_migration (SKELETOR_B200_OVERLAP=1): push() returns once its kernel is
+        # queued; the migration that completes it (count read-back, neighbour exchange,
+        # classification: three host round trips) runs on a second stream and is only
+        # waited for when something needs the particles - Sources.deposit(ions) first
+        # deposits the cells the kernel left behind and lets the exchange overlap that
+        # sweep.  Parity-checked on 8 GPUs (profiles/mgpu_check_r02_n8_*.log), but OFF by
+        # default: on 8 B200s it is 5 % slower than the in-line path (4.84 vs 4.61 ms per
+        # step; the rows inserted afterwards have to be deposited one by one).
+        self.overlap_migration = os.environ.get("SKELETOR_B200_OVERLAP", "0") == "1"
         self._pending = None
         self._side = None
         self._cnt_host = None

@@ -9,13 +9,9 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
-    "G_w4_b4_nst2": ["CS_WARPS=4", "CS_MINB=4", "CS_NST=2"],
-    "G2_w4_b5_nst2": ["CS_WARPS=4", "CS_MINB=5", "CS_NST=2"],
-    "G3_w4_b4_nst2_s32": ["CS_WARPS=4", "CS_MINB=4", "CS_NST=2", "CS_STAGE=32"],
-    "G4_w4_b4_nst2_hints": ["CS_WARPS=4", "CS_MINB=4", "CS_NST=2", "CS_L2HINTS=1"],
-    "G5_w4_b4_nst2_np2": ["CS_WARPS=4", "CS_MINB=4", "CS_NST=2", "CS_NP2=1"],
-    "G6_w4_b4_nst4_s32": ["CS_WARPS=4", "CS_MINB=4", "CS_NST=4", "CS_STAGE=32"],
-    "B2_w8_b2_nst2": ["CS_NST=2"],
+    "G_default": [],
+    "K_ins8": ["GAP_INS_ITEMS=8"],
+    "K_ins2": ["GAP_INS_ITEMS=2"],
 }
 
 if __name__ == "__main__":

@@ -57,6 +57,9 @@
 #ifndef CS_L2HINTS
 #define CS_L2HINTS 0         // particle stream: L2 evict_first; parked rows: evict_last
 #endif
+#ifndef CS_BOX32
+#define CS_BOX32 1           // stages with <= 32 particles left use the [5 x 32] box
+#endif
 #ifndef CS_HOIST_E
 #define CS_HOIST_E 1         // (CIC) the cell's E stencil lives in registers
 #endif
@@ -700,7 +703,7 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
 #define CS_FETCH(stage, j, base)                                                        \
   do {                                                                                  \
     const int fs_ = __shfl_sync(SKB_FULL, my_start, (j)) + (base);                      \
-    const bool big_ = CS_STAGE == 64 && CS_CNT(j) - (base) > 32;                        \
+    const bool big_ = CS_STAGE == 64 && (!CS_BOX32 || CS_CNT(j) - (base) > 32);         \
     if (lane == 0) {                                                                    \
       const unsigned bar_ = bar0 + 8 * (stage);                                         \
       cs_mbar_expect_tx(bar_, big_ ? 5u * 8u * 64u : 5u * 8u * 32u);                    \
@@ -756,7 +759,11 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
                                        dq, mbuf, &s_nrows, scr, scr_rows);
 #else
     {
+#if CS_BOX32
       const int pitch = (CS_STAGE == 64 && nrem > 32) ? 64 : 32;
+#else
+      constexpr int pitch = CS_STAGE;
+#endif
 #pragma unroll 1
       for (int u = 0; u < CS_STAGE / 32; u++) {
         if (u * 32 >= nrem) break;

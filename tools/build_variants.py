@@ -10,8 +10,7 @@ import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
     "G_default": [],
-    "K_ins8": ["GAP_INS_ITEMS=8"],
-    "K_ins2": ["GAP_INS_ITEMS=2"],
+    "L_box64only": ["CS_BOX32=0"],
 }
 
 if __name__ == "__main__":

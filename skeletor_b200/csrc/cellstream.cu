@@ -14,7 +14,8 @@
 //  * particles arrive through a per-warp ring of 64-particle stages, each filled by ONE
 //    TMA tensor copy (cp.async.bulk.tensor.2d + mbarrier complete_tx) of a [5 rows x 64
 //    slots] box of the [5][Nmax] particle tensor - one elected lane issues it, nobody
-//    computes per-lane load addresses; (an optional mode processes a stage as two particles
+//    computes per-lane load addresses; the tail of a cell (<= 32 particles) comes as a
+//    [5 x 32] box with the same shared-memory row pitch (3-D view, see cs_particle_map32); (an optional mode processes a stage as two particles
 //    per lane; with 128 registers per thread the compiler cannot interleave the two
 //    chains and it is slower, see CS_NP2);
 //  * all particles of a cell share the E stencil (the sort key IS the E-gather / deposit
@@ -133,6 +134,15 @@ __device__ __forceinline__ void cs_tma_load_2d(unsigned dst, const CUtensorMap *
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 #endif
+}
+// the same for a 3-D tensor (see cs_particle_map32: a [5 x 32] box laid out with the row
+// pitch of the [5 x 64] one)
+__device__ __forceinline__ void cs_tma_load_3d(unsigned dst, const CUtensorMap *tm, int c0,
+                                               int c1, int c2, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void cs_store_stream(double *p, double v) {
 #if CS_L2HINTS
@@ -706,9 +716,11 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     const bool big_ = CS_STAGE == 64 && (!CS_BOX32 || CS_CNT(j) - (base) > 32);         \
     if (lane == 0) {                                                                    \
       const unsigned bar_ = bar0 + 8 * (stage);                                         \
-      cs_mbar_expect_tx(bar_, big_ ? 5u * 8u * 64u : 5u * 8u * 32u);                    \
-      cs_tma_load_2d(ring_s + (unsigned)((stage) * CS_STAGE_D) * 8u, big_ ? &tm64 : &tm32, \
-                     fs_, 0, bar_);                                                     \
+      const unsigned dst_ = ring_s + (unsigned)((stage) * CS_STAGE_D) * 8u;             \
+      /* both boxes fill a whole [5][CS_STAGE] stage (the short one pads with zeros) */ \
+      cs_mbar_expect_tx(bar_, 5u * 8u * (unsigned)CS_STAGE);                            \
+      if (big_ || CS_STAGE == 32) cs_tma_load_2d(dst_, CS_STAGE == 64 ? &tm64 : &tm32, fs_, 0, bar_); \
+      else cs_tma_load_3d(dst_, &tm32, fs_, 0, 0, bar_);                                \
     }                                                                                   \
   } while (0)
 
@@ -755,15 +767,11 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
       cs_block<ORDER, MODIFIED, PD, 2>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
                                        dq, mbuf, &s_nrows, scr, scr_rows);
     else
-      cs_block<ORDER, MODIFIED, PD, 1>(pp, 32, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
+      cs_block<ORDER, MODIFIED, PD, 1>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
                                        dq, mbuf, &s_nrows, scr, scr_rows);
 #else
     {
-#if CS_BOX32
-      const int pitch = (CS_STAGE == 64 && nrem > 32) ? 64 : 32;
-#else
       constexpr int pitch = CS_STAGE;
-#endif
 #pragma unroll 1
       for (int u = 0; u < CS_STAGE / 32; u++) {
         if (u * 32 >= nrem) break;
@@ -890,6 +898,31 @@ static int cs_particle_map(CUtensorMap *tm, void *base, long long stride, int bo
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+// The SHORT box: [5 x 32] slots, but laid out in shared memory with the row pitch of the
+// long one, so the kernel reads both with the same immediates.  A 3-D view {slots, 1, 5} of
+// the same tensor with a box of {32, 2, 5}: the second slice of the middle dimension lies
+// outside its extent of 1 and is zero-filled by the TMA unit without touching HBM.
+static int cs_particle_map32(CUtensorMap *tm, void *base, long long stride) {
+  CUtensorMap probe;
+  int rc = cs_particle_map(&probe, base, stride, 32);       // (also resolves the entry point)
+  if (rc) return rc;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+          cudaSuccess || !fn)
+    return (int)cudaErrorNotSupported;
+  const cuuint64_t dims[3] = {(cuuint64_t)stride, 1, 5};
+  const cuuint64_t strides[2] = {(cuuint64_t)stride * sizeof(double),
+                                 (cuuint64_t)stride * sizeof(double)};
+  const cuuint32_t boxd[3] = {32, 2, 5};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((cs_encode_fn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides,
+                                  boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 // pd: 0 = push, 3 = push + full-step deposit.  Returns cudaErrorNotSupported when the
 // configuration is not the one this kernel is built for (the caller then uses the
 // generic kernel of gapped.cu): tiles other than 16 x 16, or particle arrays that are not
@@ -906,7 +939,8 @@ int cell_stream_launch(int pd, int order, int modified, skb_particles_t p, const
   CUtensorMap tm64, tm32;
   int rc = cs_particle_map(&tm64, (void *)p.x, stride, 64);
   if (rc) return rc;
-  rc = cs_particle_map(&tm32, (void *)p.x, stride, 32);
+  rc = CS_STAGE == 64 ? cs_particle_map32(&tm32, (void *)p.x, stride)
+                      : cs_particle_map(&tm32, (void *)p.x, stride, 32);
   if (rc) return rc;
   void (*k)(const CUtensorMap, const CUtensorMap, skb_particles_t, long long, const double *,
             const double *, DevGrid, GapPush, GapDeposit);

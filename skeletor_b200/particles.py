@@ -115,7 +115,12 @@ class Particles:
         i32 = dict(dtype=torch.int32, device=dev)
         # phase space coordinates, SoA: rows x, y, vx, vy, vz
         self._data = torch.zeros((5, Nmax), **f64)
-        self._alt = torch.zeros((5, Nmax), **f64)      # sort ping-pong buffer
+        # second [5][Nmax] tensor: the out-of-place tile sort, gap_build and densify ping-pong
+        # with it.  Allocated on first use and released again once the particles sit in
+        # the gapped layout (nothing needs it there): steady-state footprint of a big run
+        # = ONE particle tensor (config 5 on one GPU: 58 GB instead of 117 GB).
+        self._alt_t = None
+        self.release_sort_buffer = 40*Nmax > (1 << 30)
         self.size = Nmax
 
         self.charge = charge
@@ -215,6 +220,16 @@ class Particles:
         self._gap_start = None
         self._gap_nleft = 0
         self._gap_dirty = False
+
+    @property
+    def _alt(self):
+        if self._alt_t is None:
+            self._alt_t = torch.empty((5, self.size), dtype=torch.float64, device=self.device)
+        return self._alt_t
+
+    @_alt.setter
+    def _alt(self, t):
+        self._alt_t = t
 
     # -- particle counts ------------------------------------------------------------
     @property
@@ -417,6 +432,8 @@ class Particles:
             return False
         self._gap_fail = None
         self._data, self._alt = self._alt, self._data
+        if self.release_sort_buffer:
+            self._alt_t = None          # (the dense copy: back to the caching allocator)
         self._rep = "gapped"
         self._gap_nleft = 0
         self._gap_dirty = False

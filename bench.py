@@ -293,6 +293,7 @@ def parity_checks(sk, ions, E, B, src, dt, comm, a, n_sample=100000, band=8, mod
             full = (cand == ebits[who]).all(dim=1)
             found.index_add_(0, who[full], torch.ones_like(who[full]))
         del pos, hit
+    del lx
     if size > 1:
         found = torch.as_tensor(comm.allreduce(found.cpu().numpy(), op=sk.comm.SUM))
     n_once = int((found == 1).sum().item())
@@ -370,6 +371,7 @@ def b200_arm(a):
         xx.add_(0.05*a.nx/(2*np.pi)*torch.sin(2*np.pi*xx/a.nx))
         xx.remainder_(float(a.nx))
     ions.N = n_local
+    del d               # (no reference to the tensor: Particles swaps / releases its buffers)
     dt = 0.1*m.dx       # vt = 1  ->  vt*dt/dx = 0.1
     E = sk.Field(m, dtype=sk.Float3)
     B = sk.Field(m, dtype=sk.Float3)
@@ -829,6 +831,7 @@ def config_arm(a):
         d[2:5, :n_local] = vt*torch.randn((3, n_local), generator=gen, device=dev,
                                           dtype=torch.float64)
     ions.N = n_local
+    del d               # (no reference to the tensor: Particles swaps / releases its buffers)
     E = sk.Field(m, dtype=sk.Float3)
     B = sk.Field(m, dtype=sk.Float3)
     src = sk.Sources(m)

@@ -224,7 +224,12 @@ class Particles:
     @property
     def _alt(self):
         if self._alt_t is None:
-            self._alt_t = torch.empty((5, self.size), dtype=torch.float64, device=self.device)
+            shape = (5, self.size)
+            try:
+                self._alt_t = torch.empty(shape, dtype=torch.float64, device=self.device)
+            except torch.OutOfMemoryError:
+                torch.cuda.empty_cache()      # hand cached blocks back and try once more
+                self._alt_t = torch.empty(shape, dtype=torch.float64, device=self.device)
         return self._alt_t
 
     @_alt.setter

@@ -176,6 +176,36 @@ __device__ __forceinline__ void cs_fence_async_smem() {    // generic-proxy STS 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Shared-memory accesses of the hot loop through 32-bit shared::cta addresses with
+// immediate offsets: a generic pointer into shared memory costs a window-base computation
+// (S2UR SR_CgaCtaId / ULEA) at every use.
+template <int OFF>
+__device__ __forceinline__ double cs_lds(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void cs_sts(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+// component K of gather_cic (particle_push.pxd:21-27) from the window cell at address a
+template <int K>
+__device__ __forceinline__ double cs_cic(unsigned a, double dx, double tx, double dy, double ty) {
+  return dy * (dx * cs_lds<((CS_WS + 1) * 3 + K) * 8>(a) + tx * cs_lds<(CS_WS * 3 + K) * 8>(a)) +
+         ty * (dx * cs_lds<(3 + K) * 8>(a) + tx * cs_lds<K * 8>(a));
+}
+// component K of gather_tsc (particle_push.pxd:58-67); a = cell (iy - 1, ix - 1)
+template <int K>
+__device__ __forceinline__ double cs_tsc(unsigned a, double wmx, double w0x, double wpx,
+                                         double wmy, double w0y, double wpy) {
+  return wmy * (wmx * cs_lds<K * 8>(a) + w0x * cs_lds<(3 + K) * 8>(a) + wpx * cs_lds<(6 + K) * 8>(a)) +
+         w0y * (wmx * cs_lds<(CS_WS * 3 + K) * 8>(a) + w0x * cs_lds<(CS_WS * 3 + 3 + K) * 8>(a) +
+                wpx * cs_lds<(CS_WS * 3 + 6 + K) * 8>(a)) +
+         wpy * (wmx * cs_lds<(2 * CS_WS * 3 + K) * 8>(a) + w0x * cs_lds<(2 * CS_WS * 3 + 3 + K) * 8>(a) +
+                wpx * cs_lds<(2 * CS_WS * 3 + 6 + K) * 8>(a));
+}
+
 // ---- phase B: the rows the CTA parked in its scratch block ---------------------------
 // Rows i0 + t*256 (t < GAP_INS_ITEMS, < n) of `rows` (AoS, global): rows whose cell is one
 // of this CTA's cells [c0, c0 + CS_CELLS) are dropped into the free slots of that cell
@@ -360,7 +390,7 @@ struct CsMovers {
 template <int PD>
 __device__ __forceinline__ bool cs_stage_movers(bool mover, double x, double y, double vx,
                                                 double vy, double vz, CsMovers &mv,
-                                                double *mbuf, int *s_nrows, double *scr,
+                                                unsigned mbuf_s, int *s_nrows, double *scr,
                                                 int scr_rows, const GapPush &q) {
   const unsigned mm = __ballot_sync(SKB_FULL, mover);
   if (mm == 0) return false;
@@ -372,8 +402,8 @@ __device__ __forceinline__ bool cs_stage_movers(bool mover, double x, double y, 
   bool parked = false;
   if (after < boundary) {                             // the common case: no half completes
     if (mover) {
-      double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
-      r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+      const unsigned r = mbuf_s + (unsigned)(pos & (CS_MROWS - 1)) * 40u;
+      cs_sts<0>(r, x); cs_sts<8>(r, y); cs_sts<16>(r, vx); cs_sts<24>(r, vy); cs_sts<32>(r, vz);
     }
     mv.count = after;
     return false;
@@ -386,8 +416,8 @@ __device__ __forceinline__ bool cs_stage_movers(bool mover, double x, double y, 
     if (nxt == CS_NOSLOT && pos >= boundary) {
       parked = true;
     } else {
-      double *r = mbuf + (pos & (CS_MROWS - 1)) * 5;
-      r[0] = x; r[1] = y; r[2] = vx; r[3] = vy; r[4] = vz;
+      const unsigned r = mbuf_s + (unsigned)(pos & (CS_MROWS - 1)) * 40u;
+      cs_sts<0>(r, x); cs_sts<8>(r, y); cs_sts<16>(r, vx); cs_sts<24>(r, vy); cs_sts<32>(r, vz);
     }
   }
   const int h = (mv.count >> 5) & 1;                  // the half that is complete now
@@ -396,7 +426,7 @@ __device__ __forceinline__ bool cs_stage_movers(bool mover, double x, double y, 
   if (lane == 0) {
     double *dst = (mv.slot & CS_GLOBAL) ? q.movers + (size_t)(mv.slot & ~CS_GLOBAL) * 5
                                         : scr + (size_t)mv.slot * 5;
-    cs_bulk_store(dst, cs_smem(mbuf + h * 160), 1280u);
+    cs_bulk_store(dst, mbuf_s + (unsigned)h * 1280u, 1280u);
   }
   mv.slot = nxt;
   mv.count = nxt == CS_NOSLOT ? boundary : after;
@@ -414,14 +444,16 @@ struct CsCell {
 };
 
 template <int ORDER, bool MODIFIED, int PD, int NP>
-__device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
+__device__ __forceinline__ void cs_block(unsigned pp, int nact,
                                          CsCell<ORDER, PD> &c, CsMovers &mv,
                                          skb_particles_t P, long long pstride,
                                          const double *sE, const double *sB, double *sS,
                                          const Window &w, const double *E, const double *B,
                                          const DevGrid &g, const GapPush &q,
-                                         const GapDeposit &dq, double *mbuf, int *s_nrows,
+                                         const GapDeposit &dq, unsigned mbuf_s, int *s_nrows,
                                          double *scr, int scr_rows) {
+  // pp: shared address of this lane's first particle in the stage ([5][CS_STAGE] doubles)
+  const unsigned sE_s = cs_smem(sE), sB_s = cs_smem(sB);
   constexpr int NS = ORDER + 1;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -434,9 +466,9 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
     // idle lanes compute on a harmless particle at rest inside the cell
     x[p] = c.xsafe; y[p] = c.ysafe; vx[p] = vy[p] = vz[p] = 0.0;
     if (act[p]) {
-      const double *r = pp + p * 32;
-      x[p] = r[0]; y[p] = r[pitch]; vx[p] = r[2 * pitch]; vy[p] = r[3 * pitch];
-      vz[p] = r[4 * pitch];
+      const unsigned r = pp + (unsigned)p * 256u;
+      x[p] = cs_lds<0>(r); y[p] = cs_lds<CS_STAGE * 8>(r); vx[p] = cs_lds<2 * CS_STAGE * 8>(r);
+      vy[p] = cs_lds<3 * CS_STAGE * 8>(r); vz[p] = cs_lds<4 * CS_STAGE * 8>(r);
     }
   }
   // ---- gather + kick.  The cell promises the E base cell of its particles (the sort key)
@@ -469,19 +501,15 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
         for (int k = 0; k < 3; k++)
           e[k] = dy * (dx * c.eC[3][k] + tx * c.eC[2][k]) + ty * (dx * c.eC[1][k] + tx * c.eC[0][k]);
 #else
-        const double *ep = sE + ((c.ciy - w.y0) * CS_WS + (c.cix - w.x0)) * 3;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-          e[k] = dy * (dx * ep[(CS_WS + 1) * 3 + k] + tx * ep[CS_WS * 3 + k]) +
-                 ty * (dx * ep[3 + k] + tx * ep[k]);
+        const unsigned ep = sE_s + (unsigned)(((c.ciy - w.y0) * CS_WS + (c.cix - w.x0)) * 24);
+        e[0] = cs_cic<0>(ep, dx, tx, dy, ty); e[1] = cs_cic<1>(ep, dx, tx, dy, ty);
+        e[2] = cs_cic<2>(ep, dx, tx, dy, ty);
 #endif
-        const double *bp = sB + ((iyb[p] - w.y0) * CS_WS + (ixb[p] - w.x0)) * 3;
+        const unsigned bp = sB_s + (unsigned)(((iyb[p] - w.y0) * CS_WS + (ixb[p] - w.x0)) * 24);
         const double dxb = xb[p] - (double)ixb[p], txb = 1.0 - dxb;
         const double dyb = yb[p] - (double)iyb[p], tyb = 1.0 - dyb;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-          b[k] = dyb * (dxb * bp[(CS_WS + 1) * 3 + k] + txb * bp[CS_WS * 3 + k]) +
-                 tyb * (dxb * bp[3 + k] + txb * bp[k]);
+        b[0] = cs_cic<0>(bp, dxb, txb, dyb, tyb); b[1] = cs_cic<1>(bp, dxb, txb, dyb, tyb);
+        b[2] = cs_cic<2>(bp, dxb, txb, dyb, tyb);
       } else {
         // tsc_weights, particle_push.pxd:37-57 (xe, xb already carry the + 0.5)
         double wmx, w0x, wpx, wmy, w0y, wpy;
@@ -493,14 +521,10 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
           const double d = ye[p] - (double)iye[p] - 0.5; w0y = 0.75 - d * d;
           const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
         }
-        const double *ep = sE + ((c.ciy - 1 - w.y0) * CS_WS + (c.cix - 1 - w.x0)) * 3;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-          e[k] = wmy * (wmx * ep[k] + w0x * ep[3 + k] + wpx * ep[6 + k]) +
-                 w0y * (wmx * ep[CS_WS * 3 + k] + w0x * ep[CS_WS * 3 + 3 + k] +
-                        wpx * ep[CS_WS * 3 + 6 + k]) +
-                 wpy * (wmx * ep[2 * CS_WS * 3 + k] + w0x * ep[2 * CS_WS * 3 + 3 + k] +
-                        wpx * ep[2 * CS_WS * 3 + 6 + k]);
+        const unsigned ep = sE_s + (unsigned)(((c.ciy - 1 - w.y0) * CS_WS + (c.cix - 1 - w.x0)) * 24);
+        e[0] = cs_tsc<0>(ep, wmx, w0x, wpx, wmy, w0y, wpy);
+        e[1] = cs_tsc<1>(ep, wmx, w0x, wpx, wmy, w0y, wpy);
+        e[2] = cs_tsc<2>(ep, wmx, w0x, wpx, wmy, w0y, wpy);
         {
           const double d = xb[p] - (double)ixb[p] - 0.5; w0x = 0.75 - d * d;
           const double h = 0.5 + d; wpx = 0.5 * (h * h); wmx = 1.0 - (w0x + wpx);
@@ -509,14 +533,10 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
           const double d = yb[p] - (double)iyb[p] - 0.5; w0y = 0.75 - d * d;
           const double h = 0.5 + d; wpy = 0.5 * (h * h); wmy = 1.0 - (w0y + wpy);
         }
-        const double *bp = sB + ((iyb[p] - 1 - w.y0) * CS_WS + (ixb[p] - 1 - w.x0)) * 3;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-          b[k] = wmy * (wmx * bp[k] + w0x * bp[3 + k] + wpx * bp[6 + k]) +
-                 w0y * (wmx * bp[CS_WS * 3 + k] + w0x * bp[CS_WS * 3 + 3 + k] +
-                        wpx * bp[CS_WS * 3 + 6 + k]) +
-                 wpy * (wmx * bp[2 * CS_WS * 3 + k] + w0x * bp[2 * CS_WS * 3 + 3 + k] +
-                        wpx * bp[2 * CS_WS * 3 + 6 + k]);
+        const unsigned bp = sB_s + (unsigned)(((iyb[p] - 1 - w.y0) * CS_WS + (ixb[p] - 1 - w.x0)) * 24);
+        b[0] = cs_tsc<0>(bp, wmx, w0x, wpx, wmy, w0y, wpy);
+        b[1] = cs_tsc<1>(bp, wmx, w0x, wpx, wmy, w0y, wpy);
+        b[2] = cs_tsc<2>(bp, wmx, w0x, wpx, wmy, w0y, wpy);
       }
       rescale_and_kick<MODIFIED>(e, b, g, q.k, y[p], vx[p], vy[p], vz[p]);
     }
@@ -583,8 +603,8 @@ __device__ __forceinline__ void cs_block(const double *pp, int pitch, int nact,
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     const bool mover = !(CS_ABLATE & 1) && act[p] && !leaver[p] && !stay[p];
-    parked[p] = cs_stage_movers<PD>(mover, x[p], y[p], vx[p], vy[p], vz[p], mv, mbuf, s_nrows,
-                                    scr, scr_rows, q);
+    parked[p] = cs_stage_movers<PD>(mover, x[p], y[p], vx[p], vy[p], vz[p], mv, mbuf_s,
+                                    s_nrows, scr, scr_rows, q);
     stay[p] = stay[p] || parked[p];
   }
 #pragma unroll
@@ -694,6 +714,7 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
   double *const ring = rings + (size_t)wv * (CS_NST * CS_STAGE_D);
   const unsigned ring_s = cs_smem(ring);
   double *const mbuf = mbufs + (size_t)wv * (CS_MROWS * 5);
+  const unsigned mbuf_s = cs_smem(mbuf);
   CsMovers mv;
   mv.count = 0;
   mv.slot = cs_reserve<PD>(&s_nrows, scr_rows, q.counts, q.movers, q.mover_cap);
@@ -760,23 +781,22 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     }
     while (!cs_mbar_try_wait(bar0 + 8 * stage, (phases >> stage) & 1u)) {}
     phases ^= 1u << stage;
-    const double *pp = ring + stage * CS_STAGE_D + lane;
+    const unsigned pp = ring_s + (unsigned)(stage * CS_STAGE_D + lane) * 8u;
     const int nrem = n - cbase;
 #if CS_NP2
     if (nrem > 32)
-      cs_block<ORDER, MODIFIED, PD, 2>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
-                                       dq, mbuf, &s_nrows, scr, scr_rows);
+      cs_block<ORDER, MODIFIED, PD, 2>(pp, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q, dq,
+                                       mbuf_s, &s_nrows, scr, scr_rows);
     else
-      cs_block<ORDER, MODIFIED, PD, 1>(pp, 64, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q,
-                                       dq, mbuf, &s_nrows, scr, scr_rows);
+      cs_block<ORDER, MODIFIED, PD, 1>(pp, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q, dq,
+                                       mbuf_s, &s_nrows, scr, scr_rows);
 #else
     {
-      constexpr int pitch = CS_STAGE;
 #pragma unroll 1
       for (int u = 0; u < CS_STAGE / 32; u++) {
         if (u * 32 >= nrem) break;
-        cs_block<ORDER, MODIFIED, PD, 1>(pp + u * 32, pitch, nrem - u * 32, c, mv, P, pstride, sE,
-                                         sB, sS, w, E, B, g, q, dq, mbuf, &s_nrows, scr,
+        cs_block<ORDER, MODIFIED, PD, 1>(pp + (unsigned)u * 256u, nrem - u * 32, c, mv, P, pstride,
+                                         sE, sB, sS, w, E, B, g, q, dq, mbuf_s, &s_nrows, scr,
                                          scr_rows);
       }
     }

@@ -330,6 +330,185 @@ deposit_cells_half_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g
   flush_window(sw, w, wstride, cur, g);
 }
 
+// ---- cell-aligned deposit with a shared-memory particle ring ---------------------------
+// deposit_cells_kernel holds a chunk of particle data in registers while its loads are in
+// flight; with the 36 TSC accumulators that leaves 16 warps per SM and two chunks of
+// loads per warp, and the kernel waits on memory (long scoreboard) at half the HBM rate.
+// Here every warp streams its cells' particles through a ring of DEPR_NST stages of 64
+// particles in shared memory, filled by 8-byte cp.async two stages ahead of the stage
+// being accumulated (no registers held by loads in flight, every lane copies exactly the
+// elements it will read, so completion is per-thread: cp.async.wait_group, no barrier).
+// The stencil sums use fused multiply-adds (the deposit is compared at <= 1e-12, not bit
+// for bit: summation order already differs from the reference).
+#ifndef DEPR_NST
+#define DEPR_NST 3
+#endif
+#define DEPR_STAGE 64
+#define DEPR_STAGE_D (5 * DEPR_STAGE)
+
+__device__ __forceinline__ void depr_cp8(double *smem_dst, const double *gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int ORDER>
+__device__ __forceinline__ void accumulate_fma(Acc<ORDER + 1> &a, const double (&wx)[ORDER + 1],
+                                               const double (&wy)[ORDER + 1], double vxr,
+                                               double vy, double vz) {
+  constexpr int NS = ORDER + 1;
+#pragma unroll
+  for (int r = 0; r < NS; r++)
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+      const double wgt = wy[r] * wx[c];
+      double *v = a.v + (r * NS + c) * 4;
+      v[0] += wgt;
+      v[1] = fma(wgt, vxr, v[1]);
+      v[2] = fma(wgt, vy, v[2]);
+      v[3] = fma(wgt, vz, v[3]);
+    }
+}
+
+// position in the warp's chunk sequence: cell j (0..31, 32 = end), offset inside it
+struct DeprIt { int j, off; };
+
+template <int ORDER>
+__global__ void __launch_bounds__(DEP_THREADS, 2)
+deposit_cells_ring_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
+                          DepParams q, int parts, int wstride, int wrows) {
+  constexpr int NS = ORDER + 1;
+  extern __shared__ double sw[];
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;          // cells per CTA
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const bool gapped = tl.gap_start != nullptr;
+  const int pbeg = gapped ? tl.gap_start[c0] : (c0 ? tl.cell_end[c0 - 1] : 0);
+  const int pend = gapped ? tl.gap_start[c0 + cpp] : tl.cell_end[c0 + cpp - 1];
+  if (pbeg == pend) return;                            // uniform: no particles here
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const Window w = tile_window(tile, tl, g);
+  const int wsize = wstride * wrows * 4;
+  zero_window(sw, wsize);
+  __syncthreads();
+  double *const ring = sw + ((wsize + 1) & ~1) + wv * (DEPR_NST * DEPR_STAGE_D);
+  const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
+  // the warp's cells (at most 32, one per lane): first slot and particle count
+  const int cpw = cpp / (DEP_THREADS / 32);
+  const int wc0 = c0 + wv * cpw;
+  int my_start = 0, my_n = 0;
+  if (lane < cpw) {
+    const int cell = wc0 + lane;
+    if (gapped) { my_start = tl.gap_start[cell]; my_n = tl.gap_count[cell]; }
+    else { my_start = cell ? tl.cell_end[cell - 1] : 0; my_n = tl.cell_end[cell] - my_start; }
+  }
+  const unsigned nonempty = __ballot_sync(SKB_FULL, my_n > 0);
+  auto after = [&](int j) {                            // next non-empty cell after j
+    const unsigned m = j >= 31 ? 0u : (nonempty & ~((2u << j) - 1u));
+    return m ? __ffs(m) - 1 : 32;
+  };
+  auto advance = [&](DeprIt &it) {
+    if (it.j >= 32) return;
+    it.off += DEPR_STAGE;
+    if (it.off >= __shfl_sync(SKB_FULL, my_n, it.j)) { it.off = 0; it.j = after(it.j); }
+  };
+  auto fetch = [&](int stage, const DeprIt &it) {
+    if (it.j < 32) {
+      const int s = __shfl_sync(SKB_FULL, my_start, it.j) + it.off;
+      const int n = __shfl_sync(SKB_FULL, my_n, it.j) - it.off;
+      double *d = ring + stage * DEPR_STAGE_D;
+#pragma unroll
+      for (int u = 0; u < DEPR_STAGE / 32; u++) {
+        const int k = u * 32 + lane;
+        if (k < n) {
+          depr_cp8(d + k, P.x + s + k);
+          depr_cp8(d + DEPR_STAGE + k, P.y + s + k);
+          depr_cp8(d + 2 * DEPR_STAGE + k, P.vx + s + k);
+          depr_cp8(d + 3 * DEPR_STAGE + k, P.vy + s + k);
+          depr_cp8(d + 4 * DEPR_STAGE + k, P.vz + s + k);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // (one group per call, even empty)
+  };
+  DeprIt f, c;
+  f.j = c.j = nonempty ? __ffs(nonempty) - 1 : 32;
+  f.off = c.off = 0;
+#pragma unroll
+  for (int s = 0; s < DEPR_NST - 1; s++) { fetch(s, f); advance(f); }
+  int stage = 0;
+  Acc<NS> a;
+#pragma unroll
+  for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+  while (c.j < 32) {
+    {
+      int fs = stage + DEPR_NST - 1;
+      if (fs >= DEPR_NST) fs -= DEPR_NST;
+      fetch(fs, f);                                    // the stage consumed one turn ago
+      advance(f);
+    }
+    const int ncell = __shfl_sync(SKB_FULL, my_n, c.j);
+    const int n = ncell - c.off;
+    if (c.off == 0) {
+      const int local = (wc0 + c.j) & ((1 << cells_log2) - 1);
+      a.ix = bx + (local & ((1 << tl.tlx) - 1));
+      a.iy = by + (local >> tl.tlx);
+      // pull the particles of the cells that follow into L2, beyond the reach of the ring
+      const int nj = after(c.j);
+      const int next = nj < 32 ? __shfl_sync(SKB_FULL, my_start, nj & 31) : pend;
+      const int ahead = next + lane * 16;
+      if (ahead < min(next + 16 * DEP_PREFETCH_LINES, pend)) {
+        dep_prefetch_l2(P.x + ahead); dep_prefetch_l2(P.y + ahead);
+        dep_prefetch_l2(P.vx + ahead); dep_prefetch_l2(P.vy + ahead);
+        dep_prefetch_l2(P.vz + ahead);
+      }
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPR_NST - 1) : "memory");
+    const double *d = ring + stage * DEPR_STAGE_D;
+#pragma unroll
+    for (int u = 0; u < DEPR_STAGE / 32; u++) {
+      const int k = u * 32 + lane;
+      if (k < n) {
+        const double x = d[k], y = d[DEPR_STAGE + k], vx = d[2 * DEPR_STAGE + k];
+        const double vy = d[3 * DEPR_STAGE + k], vz = d[4 * DEPR_STAGE + k];
+        double xs = x + q.offx, ys = y + q.offy;
+        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+        int ix, iy;
+        double wx[NS], wy[NS];
+        particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+        // particle velocity relative to the background shear, deposit.pxd:24
+        const double vxr = vx + q.S * (y * g.dy + g.y0);
+        if (ix == a.ix && iy == a.iy) accumulate_fma<ORDER>(a, wx, wy, vxr, vy, vz);
+        else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, cur, g);
+      }
+    }
+    if (n <= DEPR_STAGE) {
+      // last chunk of the cell: one reduce-scatter, the NS*NS*4 sums land on as many lanes
+      const int lo = (NS == 3) ? 1 : 0;
+      const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
+                             (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
+      if constexpr (NS == 2) {
+        warp_reduce_scatter<16>(a.v, lane);
+        if (lane < 16)
+          emit_one<NS>(a.v[0], scatter_index<16>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      } else {
+        warp_reduce_scatter<32>(a.v, lane);
+        warp_reduce_scatter<4>(a.v + 32, lane);
+        emit_one<NS>(a.v[0], scatter_index<32>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        if (lane < 4)
+          emit_one<NS>(a.v[32], 32 + scatter_index<4>(lane), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      }
+#pragma unroll
+      for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+    }
+    advance(c);
+    stage = stage + 1 == DEPR_NST ? 0 : stage + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  flush_window(sw, w, wstride, cur, g);
+}
+
 // Deterministic second phase: every grid cell adds the contributions of the (up to
 // NS*NS) stencil-base cells that reach it, in a fixed order.  One thread per (cell, k).
 template <int NS>
@@ -585,7 +764,18 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
     static const int half_env = getenv("SKB_DEP_HALF") ? atoi(getenv("SKB_DEP_HALF")) : -1;
     const double ppc = (double)np / ((double)g.nx * (double)g.nyp);
     const bool half = half_env >= 0 ? half_env != 0 : ppc < 100.0;
-    if (order == 1 && half)
+    // particle ring in shared memory (SKB_DEP_RING=0 falls back to register staging); the
+    // two-cells-per-warp kernel keeps the low particle counts
+    static const int ring_env = getenv("SKB_DEP_RING") ? atoi(getenv("SKB_DEP_RING")) : -1;
+    const bool ring = cells / parts <= 32 * (DEP_THREADS / 32) && ring_env != 0;
+    if (ring && !(order == 1 && half)) {
+      const size_t rsmem = ((size_t)((ws * wr * 4 + 1) & ~1) +
+                            (size_t)(DEP_THREADS / 32) * DEPR_NST * DEPR_STAGE_D) * sizeof(double);
+      auto k = order == 1 ? deposit_cells_ring_kernel<1> : deposit_cells_ring_kernel<2>;
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      if (e != cudaSuccess) return (int)e;
+      k<<<ntiles * parts, DEP_THREADS, rsmem, st>>>(p, current, g, tl, q, parts, ws, wr);
+    } else if (order == 1 && half)
       deposit_cells_half_kernel<<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr);
     else if (order == 1)
       deposit_cells_kernel<1, false><<<ntiles * parts, DEP_THREADS, smem, st>>>(p, current, g, tl, q, parts, ws, wr, nullptr);

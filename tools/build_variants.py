@@ -9,8 +9,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
-    "G_default": [],
-    "L_box64only": ["CS_BOX32=0"],
+    "D_nst2": ["DEPR_NST=2"],
+    "D_nst4": ["DEPR_NST=4"],
 }
 
 if __name__ == "__main__":

@@ -43,3 +43,26 @@ for rep in range(3):
     torch.cuda.synchronize()
     out.append(round(e0.elapsed_time(e1), 3))
 print(os.path.basename(os.environ.get("SKELETOR_B200_LIB", "default")), out, flush=True)
+
+if os.environ.get("REPEAT"):
+    # steady state: consecutive pushes of the same particles, kernel time of each
+    times = []
+    orig = ions._gap_kernel
+
+    def timed(*a, **k):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        r = orig(*a, **k)
+        a1.record()
+        times.append((a0, a1))
+        return r
+    ions._gap_kernel = timed
+    for it in range(int(os.environ["REPEAT"])):
+        ions.push(E, B, dt)
+        if os.environ.get("PAUSE"):
+            torch.cuda.synchronize()
+            import time
+            time.sleep(float(os.environ["PAUSE"]))
+    torch.cuda.synchronize()
+    print("steady", [round(a.elapsed_time(b), 3) for a, b in times], "rep", ions._rep,
+          "fail", getattr(ions, "_gap_fail", None), flush=True)

@@ -343,6 +343,17 @@ int skb_drift_gapped(skb_particles_t p, const skb_grid_t *grid, int order, doubl
 int skb_gap_insert(const double *rows, int n, skb_particles_t p, const int *gap_start,
                    int *gap_count, const skb_grid_t *grid, int order, int tlx, int tly,
                    double *leftover, int leftover_cap, int *counts, void *stream);
+/* skb_gap_insert with the row count read on the device: min(*n_dev, nmax) rows */
+int skb_gap_insert_counted(const double *rows, const int *n_dev, int nmax, skb_particles_t p,
+                           const int *gap_start, int *gap_count, const skb_grid_t *grid,
+                           int order, int tlx, int tly, double *leftover, int leftover_cap,
+                           int *counts, void *stream);
+/* One migration message of cppmove2 (pplib2.c:741-753: count + particle rows to a
+ * neighbour) written straight into the neighbour's receive slot `dst` (peer memory):
+ * dst[0] = n = min(*count, max_rows), dst[1..4] = 0, dst[5..] = the n AoS rows; the
+ * count is read on the device, so no host synchronisation precedes the send. */
+int skb_peer_send(const double *rows, const int *count, int max_rows, double *dst,
+                  void *stream);
 int skb_gap_densify(skb_particles_t in, skb_particles_t out, const int *gap_start,
                     const int *gap_count, const skb_grid_t *grid, int tlx, int tly,
                     int *dense_start, int *cell_end, int *tile_offsets, int *block_sums,

@@ -97,6 +97,9 @@ SIGNATURES = {
     "skb_deposit_rows": [c_vp, c_int, c_vp, _G, c_int, c_dbl, c_vp],
     "skb_gap_insert": [c_vp, c_int, _P, c_vp, c_vp, _G, c_int, c_int, c_int, c_vp, c_int,
                        c_vp, c_vp],
+    "skb_gap_insert_counted": [c_vp, c_vp, c_int, _P, c_vp, c_vp, _G, c_int, c_int, c_int,
+                               c_vp, c_int, c_vp, c_vp],
+    "skb_peer_send": [c_vp, c_vp, c_int, c_vp, c_vp],
     "skb_gap_densify": [_P, _P, c_vp, c_vp, _G, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                         c_vp, c_int, c_int, c_ll, c_vp],
     "skb_exclusive_scan": [c_vp, c_int, c_vp, c_vp],

@@ -507,6 +507,56 @@ extern "C" int skb_gap_densify(skb_particles_t in, skb_particles_t out, const in
   return 0;
 }
 
+// the same with the row count read on the device (no host round trip between the kernel
+// that produced the rows and their insertion): a fixed grid strides over the rows
+__global__ void __launch_bounds__(256)
+gap_insert_counted_kernel(const double *__restrict__ rows, const int *__restrict__ n_dev,
+                          int nmax, skb_particles_t P, const int *__restrict__ gap_start,
+                          int *gap_count, KeyParams kp, double *leftover, int leftover_cap,
+                          int *counts) {
+  const int n = min(*n_dev, nmax);
+  const int per = 256 * GAP_INS_ITEMS;
+  for (int b = blockIdx.x; (long long)b * per < n; b += gridDim.x)
+    gap_insert_rows(rows, n, b * per + threadIdx.x, P, gap_start, gap_count, kp, leftover,
+                    leftover_cap, counts);
+}
+
+extern "C" int skb_gap_insert_counted(const double *rows, const int *n_dev, int nmax,
+                                      skb_particles_t p, const int *gap_start,
+                                      int *gap_count, const skb_grid_t *grid, int order,
+                                      int tlx, int tly, double *leftover, int leftover_cap,
+                                      int *counts, void *stream) {
+  if (nmax <= 0) return 0;
+  DevGrid g = make_grid(grid);
+  KeyParams kp = make_keyparams(g, order, tlx, tly);
+  const int per = 256 * GAP_INS_ITEMS;
+  const int nblk = (int)min((long long)(nmax + per - 1) / per, 148LL * 16);
+  gap_insert_counted_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(
+      rows, n_dev, nmax, p, gap_start, gap_count, kp, leftover, leftover_cap, counts);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Migration message into a neighbour's receive slot (peer memory over NVLink, or local):
+// header row {count, 0, 0, 0, 0} + count rows, the count read on the device
+// (pplib2.c:741-753 sends the count in a message of its own).
+__global__ void __launch_bounds__(256)
+peer_send_kernel(const double *__restrict__ rows, const int *__restrict__ count,
+                 int max_rows, double *__restrict__ dst) {
+  const int n = min(max(*count, 0), max_rows);
+  const long long nd = (long long)n * 5;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 < 5) dst[i0] = i0 == 0 ? (double)n : 0.0;
+  for (long long i = i0; i < nd; i += (long long)gridDim.x * blockDim.x) dst[5 + i] = rows[i];
+}
+
+extern "C" int skb_peer_send(const double *rows, const int *count, int max_rows, double *dst,
+                             void *stream) {
+  peer_send_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(rows, count, max_rows, dst);
+  SKB_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int skb_gap_insert(const double *rows, int n, skb_particles_t p,
                               const int *gap_start, int *gap_count, const skb_grid_t *grid,
                               int order, int tlx, int tly, double *leftover,

@@ -141,10 +141,16 @@ class Particles:
         from . import peer
         self._mig = peer.PeerArena(manifold.comm, (nbmax + 1)*5) \
             if peer.available(manifold.comm) else None
+        if self._mig is None and getattr(manifold.comm, "size", 1) == 1 and \
+                os.environ.get("SKELETOR_B200_PEER", "1") != "0":
+            # one rank: the same device-counted migration through a local arena (only
+            # the gapped push uses it, see _gap_finish_single_sync)
+            self._mig = peer.LocalArena((nbmax + 1)*5, self.device)
         self.rbufl = torch.zeros((nbmax, 5), **f64)
         self.rbufr = torch.zeros((nbmax, 5), **f64)
         self._keep = torch.zeros((2*nbmax, 5), **f64)
         self._counts = torch.zeros(8, **i32)
+        self._counts_b = torch.zeros(8, **i32)
         self._move_scratch = torch.zeros(2*ntmax + 8, **i32)
         self._ihole_scratch = torch.zeros(
             int(_lib.load().skb_ihole_scratch_ints(Nmax)) + 1, **i32)
@@ -188,8 +194,6 @@ class Particles:
         # been touched in between.  "auto": switched on by the first deposit that follows a
         # push, switched off again when a fused result goes unused.  OFF by default: on
         # config 5 the fused sweep takes 50 ms against 23.7 + 7.5 ms for the two kernels
-        # (register pressure of the two roles in one kernel).  OFF by default: on
-        # config 5 the fused sweep takes 50 ms against 23.7 + 7.5 ms for the two kernels
         # (register pressure of the two roles in one kernel).
         self.fuse_deposit = os.environ.get("SKELETOR_B200_FUSE", "0")
         if self.fuse_deposit in ("0", "1"):
@@ -209,6 +213,11 @@ class Particles:
         # default: on 8 B200s it is 5 % slower than the in-line path (4.84 vs 4.61 ms per
         # step; the rows inserted afterwards have to be deposited one by one).
         self.overlap_migration = os.environ.get("SKELETOR_B200_OVERLAP", "0") == "1"
+        # single_sync (SKELETOR_B200_SINGLE_SYNC=0 turns it off): with the NVLink peer
+        # arena the whole migration of a gapped push - send, classify, insert - is queued
+        # behind the push kernel with device-side counts and the host reads all counters
+        # in ONE synchronisation at the end (three before)
+        self.single_sync = os.environ.get("SKELETOR_B200_SINGLE_SYNC", "1") != "0"
         self._pending = None
         self._side = None
         self._cnt_host = None
@@ -614,13 +623,64 @@ class Particles:
                                    self._movers.shape[0]))
 
     def _gap_finish(self, cnt, cfl=False, fused=False):
+        if self._mig is not None and self.single_sync and not fused:
+            return self._gap_finish_single_sync(cnt, cfl)
         nm, nl, nr, fl, nlocal = cnt[:5].tolist()
         self._gap_check_flags(fl, cfl)
         nkeep = self._exchange(nl, nr)
         self._gap_finish_tail(nm, nl, nr, fl, nlocal, nkeep, fused)
 
+    def _gap_finish_single_sync(self, cnt, cfl=False):
+        """_gap_finish through NVLink peer memory with ONE host synchronisation: the
+        leavers are sent with device-side counts (skb_peer_send), classified from the
+        message headers, movers and arrivals are inserted with device-side counts
+        (skb_gap_insert_counted), and only then the host reads every counter of the step.
+        Everything is queued while the push kernel runs, so the migration costs the GPU
+        its kernels and one barrier, not the host's launch latencies."""
+        m = self.manifold
+        comm = m.comm
+        st = _stream()
+        arena = self._mig
+        c2 = self._counts_b
+        p0 = cnt.data_ptr()
+        # cnt = (rows on the mover list, leavers down, leavers up, flags, ...)
+        from_below, from_above = arena.exchange_counted(self.sbufr, p0 + 8, self.sbufl, p0 + 4,
+                                                        self.nbmax)
+        c2.zero_()
+        for buf in (from_below, from_above):
+            _lib.call("skb_move_classify", buf.data_ptr(), -(self.nbmax + 1),
+                      self._keep.data_ptr(), self.sbufl.data_ptr(),
+                      self.sbufr.data_ptr(), self.nbmax, c2.data_ptr(), m.c,
+                      comm.rank, comm.size, st)
+        flags = arena.all_flags((c2[1] + c2[2]) > 0)
+        g = self._gcnt          # (reset by skb_push_gapped)
+        for rows, nptr in ((self._movers, p0), (self._keep, c2.data_ptr())):
+            _lib.call("skb_gap_insert_counted", rows.data_ptr(), nptr, rows.shape[0],
+                      self._c, self._gap_start.data_ptr(), self._gap_count.data_ptr(), m.c,
+                      self.order, TLX, TLY, self._leftover.data_ptr(),
+                      self._leftover.shape[1], g.data_ptr(), st)
+        vals = torch.cat([cnt[:5], c2[:4], g[:2], flags.to(torch.int32)]).tolist()
+        nm, nl, nr, fl, nlocal, nkeep, fnl, fnr, ovf, nleft, lost = vals[:11]
+        self._gap_check_flags(fl, cfl)
+        if ovf or nkeep > self._keep.shape[0]:
+            raise RuntimeError("particle buffer overflow while forwarding")
+        self.info[4] = max(self.info[4], 1)
+        if any(vals[11:]):
+            # somebody still forwards particles (more than one slab crossed in a step):
+            # the remaining rounds of cppmove2 (pplib2.c:708-866), then their arrivals
+            nkeep2 = self._exchange_peer(fnl, fnr, nkeep=nkeep, first=1)
+            _lib.call("skb_gap_insert", self._keep[nkeep:].data_ptr(), nkeep2 - nkeep,
+                      self._c, self._gap_start.data_ptr(), self._gap_count.data_ptr(), m.c,
+                      self.order, TLX, TLY, self._leftover.data_ptr(),
+                      self._leftover.shape[1], g.data_ptr(), st)
+            nleft, lost = g[:2].tolist()
+            nkeep = nkeep2
+        self._gap_finish_tail(nm, nl, nr, fl, nlocal, nkeep, False, inserted=(nleft, lost))
+
     def _gap_finish_tail(self, nm, nl, nr, fl, nlocal, nkeep, fused, deposit_into=None,
-                         nleft_b=0):
+                         nleft_b=0, inserted=None):
+        """inserted: (leftover rows, overflow flag) when movers and arrivals have been
+        inserted already (_gap_finish_single_sync)"""
         m = self.manifold
         st = _stream()
         if deposit_into is not None:
@@ -648,13 +708,16 @@ class Particles:
             raise RuntimeError("particle overflow error, ierr = {}".format(
                 new_n - self.size))
         g = self._gcnt          # (reset by skb_push_gapped)
-        for rows, n in ((self._movers, min(nm, self._movers.shape[0])),
-                        (self._keep, nkeep)):
-            _lib.call("skb_gap_insert", rows.data_ptr(), n, self._c,
-                      self._gap_start.data_ptr(), self._gap_count.data_ptr(), m.c,
-                      self.order, TLX, TLY, self._leftover.data_ptr(),
-                      self._leftover.shape[1], g.data_ptr(), st)
-        nleft, lost = g[:2].tolist()
+        if inserted is None:
+            for rows, n in ((self._movers, min(nm, self._movers.shape[0])),
+                            (self._keep, nkeep)):
+                _lib.call("skb_gap_insert", rows.data_ptr(), n, self._c,
+                          self._gap_start.data_ptr(), self._gap_count.data_ptr(), m.c,
+                          self.order, TLX, TLY, self._leftover.data_ptr(),
+                          self._leftover.shape[1], g.data_ptr(), st)
+            nleft, lost = g[:2].tolist()
+        else:
+            nleft, lost = inserted
         if lost:
             raise RuntimeError("gapped layout: leftover list overflow "
                                "({} > {})".format(nleft, self._leftover.shape[1]))
@@ -747,7 +810,7 @@ class Particles:
         st = _stream()
         cnt = self._counts
         nkeep = 0
-        if self._mig is not None:
+        if self._mig is not None and not self._mig.local:
             return self._exchange_peer(nl, nr)
         for it in range(2000):
             self.info[4] = max(self.info[4], it + 1)     # passes, pplib2.c:955
@@ -783,7 +846,7 @@ class Particles:
                 break
         return nkeep
 
-    def _exchange_peer(self, nl, nr):
+    def _exchange_peer(self, nl, nr, nkeep=0, first=0):
         """_exchange through NVLink peer memory: header + rows are copied straight into
         the neighbours' slots, one device-side barrier, classification with device-side
         counts, and the "does anybody still forward?" agreement (cppimax, pplib2.c:873)
@@ -794,8 +857,7 @@ class Particles:
         st = _stream()
         cnt = self._counts
         arena = self._mig
-        nkeep = 0
-        for it in range(2000):
+        for it in range(first, 2000):
             self.info[4] = max(self.info[4], it + 1)     # passes, pplib2.c:955
             self._sbl[0, :1].fill_(float(nl))
             self._sbr[0, :1].fill_(float(nr))

@@ -48,6 +48,7 @@ def available(comm):
 class PeerArena:
     """2 (parity) x 2 (from_below, from_above) slots of `slot_doubles` float64 each,
     plus 2 x size flag words, in symmetric memory."""
+    local = False
 
     def __init__(self, comm, slot_doubles):
         import torch.distributed as dist
@@ -89,6 +90,27 @@ class PeerArena:
         o0, o1 = self._slot(p, 0), self._slot(p, 1)
         return self.t[o0:o0 + self.cap], self.t[o1:o1 + self.cap]
 
+    def exchange_counted(self, up_rows, up_count, down_rows, down_count, max_rows):
+        """exchange() for migration messages whose row counts live on the device:
+        `up_rows` / `down_rows` are AoS row buffers ([max_rows][5] float64), `up_count` /
+        `down_count` device addresses of their int32 row counts.  skb_peer_send writes
+        header row + rows straight into the neighbours' slots, so the host does not
+        have to know the counts (no synchronisation before the send)."""
+        from . import _lib
+        from .field import _stream
+        p = self.k & 1
+        self.k += 1
+        st = _stream()
+        o = self._slot(p, 0)
+        _lib.call("skb_peer_send", up_rows.data_ptr(), up_count, max_rows,
+                  self.above_buf[o:].data_ptr(), st)
+        o = self._slot(p, 1)
+        _lib.call("skb_peer_send", down_rows.data_ptr(), down_count, max_rows,
+                  self.below_buf[o:].data_ptr(), st)
+        self.hdl.barrier()
+        o0, o1 = self._slot(p, 0), self._slot(p, 1)
+        return self.t[o0:o0 + self.cap], self.t[o1:o1 + self.cap]
+
     def all_flags(self, flag):
         """every rank publishes one float64 device scalar to all ranks; returns the
         local view [size] of everybody's value after a barrier (no host sync)"""
@@ -101,3 +123,26 @@ class PeerArena:
         self.hdl.barrier()
         o = 4*self.cap + p*self.size
         return self.t[o:o + self.size]
+
+
+class _NoBarrier:
+    def barrier(self):
+        pass
+
+
+class LocalArena(PeerArena):
+    """The arena of a single rank: both neighbours are the rank itself (nvp == 1,
+    pplib2.c:715-730), the slots are ordinary device memory and the barrier is stream
+    order.  Lets one-rank runs use the same device-counted migration as N ranks."""
+    local = True
+
+    def __init__(self, slot_doubles, device):
+        self.comm = None
+        self.cap = int(slot_doubles)
+        self.size, self.rank = 1, 0
+        self.nflag = 2
+        self.t = torch.zeros(4*self.cap + self.nflag, dtype=torch.float64, device=device)
+        self.above_buf = self.below_buf = self.t
+        self.all_bufs = [self.t]
+        self.k = 0
+        self.hdl = _NoBarrier()

@@ -509,6 +509,198 @@ deposit_cells_ring_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g
   flush_window(sw, w, wstride, cur, g);
 }
 
+// ---- two cells per warp + particle ring --------------------------------------------------
+// deposit_cells_ring_kernel with every half-warp on a cell of its own (cells 2i and 2i+1 of
+// the warp's block advance together): one reduce-scatter over 16 lanes and one emit serve
+// TWO cells, which halves the per-cell reduction work — a quarter of the TSC kernel's
+// instructions at 256 particles per cell, and as much as the accumulation itself below
+// ~100 particles per cell.  Ring stage = 32 particles per half-warp.
+#define DEPP_CHUNK 32
+#define DEPP_STAGE_D (2 * 5 * DEPP_CHUNK)
+
+// Reduce-scatter of V values over the 16 lanes of each half-warp.  V = 16: v[0] of lane hl
+// = value half_scatter_index<16>(hl); V = 32: v[0], v[1] = values half_scatter_index<32>(hl)
+// + {0, 1}; V = 4: v[0] = value half_scatter_index<4>(hl) (replicated over hl >> 2).
+template <int V>
+__device__ __forceinline__ int half_scatter_index(int hl) {
+  int idx = 0;
+#pragma unroll
+  for (int s = 0, h = V / 2; h >= 1 && s < 4; s++, h >>= 1) idx += ((hl >> s) & 1) * h;
+  return idx;
+}
+template <int V>
+__device__ __forceinline__ void half_reduce_scatter(double *v, int lane) {
+  int bit = 1;
+#pragma unroll
+  for (int h = V / 2; h >= 1 && bit < 16; h >>= 1, bit <<= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < h; j++) {
+      const double a = v[j], b = v[j + h];
+      const double send = up ? a : b;
+      const double keep = up ? b : a;
+      v[j] = keep + __shfl_xor_sync(SKB_FULL, send, bit);
+    }
+  }
+#pragma unroll
+  for (; bit < 16; bit <<= 1) v[0] += __shfl_xor_sync(SKB_FULL, v[0], bit);
+}
+
+struct DeppIt { int i, c; };      // pair of cells (0..15, 16 = end), chunk inside it
+
+template <int ORDER>
+__global__ void __launch_bounds__(DEP_THREADS, 2)
+deposit_cells_pair_kernel(skb_particles_t P, double *__restrict__ cur, DevGrid g, DevTiling tl,
+                          DepParams q, int parts, int wstride, int wrows) {
+  constexpr int NS = ORDER + 1;
+  extern __shared__ double sw[];
+  const int cells_log2 = tl.tlx + tl.tly;
+  const int cpp = (1 << cells_log2) / parts;          // cells per CTA
+  const int tile = blockIdx.x / parts;
+  const int c0 = (tile << cells_log2) + (blockIdx.x % parts) * cpp;
+  const bool gapped = tl.gap_start != nullptr;
+  const int pbeg = gapped ? tl.gap_start[c0] : (c0 ? tl.cell_end[c0 - 1] : 0);
+  const int pend = gapped ? tl.gap_start[c0 + cpp] : tl.cell_end[c0 + cpp - 1];
+  if (pbeg == pend) return;                            // uniform: no particles here
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int half = lane >> 4, hl = lane & 15;
+  const Window w = tile_window(tile, tl, g);
+  const int wsize = wstride * wrows * 4;
+  zero_window(sw, wsize);
+  __syncthreads();
+  double *const ring = sw + ((wsize + 1) & ~1) + wv * (DEPR_NST * DEPP_STAGE_D) +
+                       half * (5 * DEPP_CHUNK);
+  const int bx = (tile % tl.ntx) << tl.tlx, by = (tile / tl.ntx) << tl.tly;
+  // the warp's cells (at most 32, one per lane): first slot and particle count
+  const int cpw = cpp / (DEP_THREADS / 32);
+  const int wc0 = c0 + wv * cpw;
+  int my_start = 0, my_n = 0;
+  if (lane < cpw) {
+    const int cell = wc0 + lane;
+    if (gapped) { my_start = tl.gap_start[cell]; my_n = tl.gap_count[cell]; }
+    else { my_start = cell ? tl.cell_end[cell - 1] : 0; my_n = tl.cell_end[cell] - my_start; }
+  }
+  // lane i < 16: chunks of pair i = those of its bigger cell
+  const int na = __shfl_sync(SKB_FULL, my_n, (2 * lane) & 31);
+  const int nb = __shfl_sync(SKB_FULL, my_n, (2 * lane + 1) & 31);
+  const int my_nch = lane < 16 ? (max(na, nb) + DEPP_CHUNK - 1) / DEPP_CHUNK : 0;
+  const unsigned nonempty = __ballot_sync(SKB_FULL, my_nch > 0);
+  auto after = [&](int i) {                            // next non-empty pair after i
+    const unsigned m = nonempty & ~((2u << i) - 1u);
+    return m ? __ffs(m) - 1 : 16;
+  };
+  auto advance = [&](DeppIt &it) {
+    if (it.i >= 16) return;
+    it.c += 1;
+    if (it.c >= __shfl_sync(SKB_FULL, my_nch, it.i)) { it.c = 0; it.i = after(it.i); }
+  };
+  auto fetch = [&](int stage, const DeppIt &it) {
+    if (it.i < 16) {
+      const int cell = 2 * it.i + half;
+      const int s = __shfl_sync(SKB_FULL, my_start, cell) + it.c * DEPP_CHUNK;
+      const int n = __shfl_sync(SKB_FULL, my_n, cell) - it.c * DEPP_CHUNK;
+      double *d = ring + stage * DEPP_STAGE_D;
+#pragma unroll
+      for (int u = 0; u < DEPP_CHUNK / 16; u++) {
+        const int k = u * 16 + hl;
+        if (k < n) {
+          depr_cp8(d + k, P.x + s + k);
+          depr_cp8(d + DEPP_CHUNK + k, P.y + s + k);
+          depr_cp8(d + 2 * DEPP_CHUNK + k, P.vx + s + k);
+          depr_cp8(d + 3 * DEPP_CHUNK + k, P.vy + s + k);
+          depr_cp8(d + 4 * DEPP_CHUNK + k, P.vz + s + k);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // (one group per call, even empty)
+  };
+  DeppIt f, c;
+  f.i = c.i = nonempty ? __ffs(nonempty) - 1 : 16;
+  f.c = c.c = 0;
+#pragma unroll
+  for (int s = 0; s < DEPR_NST - 1; s++) { fetch(s, f); advance(f); }
+  int stage = 0;
+  Acc<NS> a;
+#pragma unroll
+  for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+  a.ix = a.iy = 0;
+  int ncell = 0;
+  while (c.i < 16) {
+    {
+      int fs = stage + DEPR_NST - 1;
+      if (fs >= DEPR_NST) fs -= DEPR_NST;
+      fetch(fs, f);                                    // the stage consumed one turn ago
+      advance(f);
+    }
+    const int nch = __shfl_sync(SKB_FULL, my_nch, c.i);
+    if (c.c == 0) {
+      const int cl = 2 * c.i + half;                   // my half's cell of this pair
+      ncell = __shfl_sync(SKB_FULL, my_n, cl);
+      const int local = (wc0 + min(cl, cpw - 1)) & ((1 << cells_log2) - 1);
+      a.ix = bx + (local & ((1 << tl.tlx) - 1));
+      a.iy = by + (local >> tl.tlx);
+      // pull my half's next cell into L2, beyond the reach of the ring
+      const int nx2 = min(cl + 2, 31);
+      const int s2 = __shfl_sync(SKB_FULL, my_start, nx2);
+      const int n2 = __shfl_sync(SKB_FULL, my_n, nx2);
+      if (cl + 2 < cpw && hl * 16 < n2) {
+        const int ahead = s2 + hl * 16;
+        dep_prefetch_l2(P.x + ahead); dep_prefetch_l2(P.y + ahead);
+        dep_prefetch_l2(P.vx + ahead); dep_prefetch_l2(P.vy + ahead);
+        dep_prefetch_l2(P.vz + ahead);
+      }
+    }
+    const int n = ncell - c.c * DEPP_CHUNK;
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPR_NST - 1) : "memory");
+    const double *d = ring + stage * DEPP_STAGE_D;
+#pragma unroll
+    for (int u = 0; u < DEPP_CHUNK / 16; u++) {
+      const int k = u * 16 + hl;
+      if (k < n) {
+        const double x = d[k], y = d[DEPP_CHUNK + k], vx = d[2 * DEPP_CHUNK + k];
+        const double vy = d[3 * DEPP_CHUNK + k], vz = d[4 * DEPP_CHUNK + k];
+        double xs = x + q.offx, ys = y + q.offy;
+        if (ORDER == 2) { xs = xs + 0.5; ys = ys + 0.5; }
+        int ix, iy;
+        double wx[NS], wy[NS];
+        particle_terms<ORDER>(xs, ys, ix, iy, wx, wy);
+        // particle velocity relative to the background shear, deposit.pxd:24
+        const double vxr = vx + q.S * (y * g.dy + g.y0);
+        if (ix == a.ix && iy == a.iy) accumulate_fma<ORDER>(a, wx, wy, vxr, vy, vz);
+        else single_particle_emit<NS>(wx, wy, ix, iy, vxr, vy, vz, cur, g);
+      }
+    }
+    if (c.c + 1 >= nch) {
+      // last chunk of the pair: one reduce-scatter for both cells
+      const int lo = (NS == 3) ? 1 : 0;
+      const bool in_window = (a.ix - lo >= w.x0) && (a.ix - lo + NS <= w.x1) &&
+                             (a.iy - lo >= w.y0) && (a.iy - lo + NS <= w.y1);
+      if constexpr (NS == 2) {
+        half_reduce_scatter<16>(a.v, lane);
+        if (ncell > 0)
+          emit_one<NS>(a.v[0], half_scatter_index<16>(hl), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+      } else {
+        half_reduce_scatter<32>(a.v, lane);
+        half_reduce_scatter<4>(a.v + 32, lane);
+        if (ncell > 0) {
+          const int i0 = half_scatter_index<32>(hl);
+          emit_one<NS>(a.v[0], i0, in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+          emit_one<NS>(a.v[1], i0 + 1, in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+          if (hl < 4)
+            emit_one<NS>(a.v[32], 32 + half_scatter_index<4>(hl), in_window, a.ix, a.iy, sw, w, wstride, cur, g);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS * NS * 4; i++) a.v[i] = 0.0;
+    }
+    advance(c);
+    stage = stage + 1 == DEPR_NST ? 0 : stage + 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  flush_window(sw, w, wstride, cur, g);
+}
+
 // Deterministic second phase: every grid cell adds the contributions of the (up to
 // NS*NS) stencil-base cells that reach it, in a fixed order.  One thread per (cell, k).
 template <int NS>
@@ -768,7 +960,17 @@ static int deposit_impl(skb_particles_t p, long long np, double *current,
     // two-cells-per-warp kernel keeps the low particle counts
     static const int ring_env = getenv("SKB_DEP_RING") ? atoi(getenv("SKB_DEP_RING")) : -1;
     const bool ring = cells / parts <= 32 * (DEP_THREADS / 32) && ring_env != 0;
-    if (ring && !(order == 1 && half)) {
+    // two cells per warp: TSC and few particles per cell (SKB_DEP_PAIR=0/1 overrides)
+    static const int pair_env = getenv("SKB_DEP_PAIR") ? atoi(getenv("SKB_DEP_PAIR")) : -1;
+    const bool pair = ring && (pair_env >= 0 ? pair_env != 0 : (order == 2 || half));
+    if (pair) {
+      const size_t rsmem = ((size_t)((ws * wr * 4 + 1) & ~1) +
+                            (size_t)(DEP_THREADS / 32) * DEPR_NST * DEPP_STAGE_D) * sizeof(double);
+      auto k = order == 1 ? deposit_cells_pair_kernel<1> : deposit_cells_pair_kernel<2>;
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      if (e != cudaSuccess) return (int)e;
+      k<<<ntiles * parts, DEP_THREADS, rsmem, st>>>(p, current, g, tl, q, parts, ws, wr);
+    } else if (ring && !(order == 1 && half)) {
       const size_t rsmem = ((size_t)((ws * wr * 4 + 1) & ~1) +
                             (size_t)(DEP_THREADS / 32) * DEPR_NST * DEPR_STAGE_D) * sizeof(double);
       auto k = order == 1 ? deposit_cells_ring_kernel<1> : deposit_cells_ring_kernel<2>;

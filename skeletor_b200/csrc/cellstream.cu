@@ -448,12 +448,13 @@ __device__ __forceinline__ void cs_block(unsigned pp, int nact,
                                          CsCell<ORDER, PD> &c, CsMovers &mv,
                                          skb_particles_t P, long long pstride,
                                          const double *sE, const double *sB, double *sS,
+                                         unsigned sE_s, unsigned sB_s,
                                          const Window &w, const double *E, const double *B,
                                          const DevGrid &g, const GapPush &q,
                                          const GapDeposit &dq, unsigned mbuf_s, int *s_nrows,
                                          double *scr, int scr_rows) {
-  // pp: shared address of this lane's first particle in the stage ([5][CS_STAGE] doubles)
-  const unsigned sE_s = cs_smem(sE), sB_s = cs_smem(sB);
+  // pp: shared address of this lane's first particle in the stage ([5][CS_STAGE] doubles);
+  // sE_s, sB_s: shared addresses of the field windows sE, sB
   constexpr int NS = ORDER + 1;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -712,9 +713,15 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
   double *const scr = s_blk >= 0 ? q.scratch + (size_t)s_blk * q.scratch_rows * 5 : nullptr;
   const int scr_rows = s_blk >= 0 ? (q.scratch_rows & ~31) : 0;    // whole halves only
   double *const ring = rings + (size_t)wv * (CS_NST * CS_STAGE_D);
-  const unsigned ring_s = cs_smem(ring);
   double *const mbuf = mbufs + (size_t)wv * (CS_MROWS * 5);
-  const unsigned mbuf_s = cs_smem(mbuf);
+  // The shared-window base, made opaque so that it lives in ONE register: the compiler
+  // otherwise recomputes it (S2R SR_CgaCtaId + shifts) in front of every shared access.
+  unsigned sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(cs_smem(smem)));
+  const unsigned ring_s = sbase + (unsigned)((ring - smem) * sizeof(double));
+  const unsigned mbuf_s = sbase + (unsigned)((mbuf - smem) * sizeof(double));
+  const unsigned sE_s = sbase + (unsigned)((sE - smem) * sizeof(double));
+  const unsigned sB_s = sbase + (unsigned)((sB - smem) * sizeof(double));
   CsMovers mv;
   mv.count = 0;
   mv.slot = cs_reserve<PD>(&s_nrows, scr_rows, q.counts, q.movers, q.mover_cap);
@@ -785,19 +792,19 @@ cell_stream_kernel(const __grid_constant__ CUtensorMap tm64,
     const int nrem = n - cbase;
 #if CS_NP2
     if (nrem > 32)
-      cs_block<ORDER, MODIFIED, PD, 2>(pp, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q, dq,
-                                       mbuf_s, &s_nrows, scr, scr_rows);
+      cs_block<ORDER, MODIFIED, PD, 2>(pp, nrem, c, mv, P, pstride, sE, sB, sS, sE_s, sB_s, w, E, B,
+                                       g, q, dq, mbuf_s, &s_nrows, scr, scr_rows);
     else
-      cs_block<ORDER, MODIFIED, PD, 1>(pp, nrem, c, mv, P, pstride, sE, sB, sS, w, E, B, g, q, dq,
-                                       mbuf_s, &s_nrows, scr, scr_rows);
+      cs_block<ORDER, MODIFIED, PD, 1>(pp, nrem, c, mv, P, pstride, sE, sB, sS, sE_s, sB_s, w, E, B,
+                                       g, q, dq, mbuf_s, &s_nrows, scr, scr_rows);
 #else
     {
 #pragma unroll 1
       for (int u = 0; u < CS_STAGE / 32; u++) {
         if (u * 32 >= nrem) break;
         cs_block<ORDER, MODIFIED, PD, 1>(pp + (unsigned)u * 256u, nrem - u * 32, c, mv, P, pstride,
-                                         sE, sB, sS, w, E, B, g, q, dq, mbuf_s, &s_nrows, scr,
-                                         scr_rows);
+                                         sE, sB, sS, sE_s, sB_s, w, E, B, g, q, dq, mbuf_s,
+                                         &s_nrows, scr, scr_rows);
       }
     }
 #endif

@@ -62,6 +62,39 @@ def test_push_bitexact(gk, order, modified, sort):
         assert np.array_equal(bits(got), bits(exp))
 
 
+@pytest.mark.parametrize("count", [0, 37, 64, 1000])
+def test_peer_send(count):
+    """skb_peer_send: header {n, 0, 0, 0, 0} + n = min(count, max_rows) rows, the count read
+    on the device; nothing beyond the message is written"""
+    max_rows = 64
+    rng = np.random.default_rng(9)
+    rows = torch.as_tensor(rng.normal(size=(max_rows, 5)), device="cuda")
+    cnt = torch.tensor([count], dtype=torch.int32, device="cuda")
+    dst = torch.full((5*(max_rows + 2),), -7.0, dtype=torch.float64, device="cuda")
+    _lib.call("skb_peer_send", rows.data_ptr(), cnt.data_ptr(), max_rows, dst.data_ptr(),
+              gu.stream())
+    n = min(count, max_rows)
+    out = dst.cpu().numpy()
+    assert out[0] == n and np.all(out[1:5] == 0)
+    assert np.array_equal(out[5:5 + 5*n], rows.cpu().numpy().reshape(-1)[:5*n])
+    assert np.all(out[5 + 5*n:] == -7.0)
+
+
+@pytest.mark.parametrize("env", [{"SKB_DEP_RING": "0"}, {"SKB_DEP_PAIR": "0"},
+                                 {"SKB_DEP_PAIR": "1"}])
+def test_deposit_kernel_variants(env):
+    """the deposit kernels the default selection does not pick (register staging; one cell
+    per warp for TSC / few particles; two cells per warp for CIC at 256 per cell) stay
+    correct: tests/dep_variants_check.py in a subprocess, the selection is per process"""
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dep_variants_check.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, **env})
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("gk", GRIDS[:3])
 @pytest.mark.parametrize("shear", [False, True])
 def test_push_epilogue_matches_reference_sequence(gk, shear):

@@ -9,8 +9,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
-    "D_nst2": ["DEPR_NST=2"],
-    "D_nst4": ["DEPR_NST=4"],
+    "H0M5": ["CS_HOIST_E=0", "CS_MINB=5"],
+    "H0M4": ["CS_HOIST_E=0"],
 }
 
 if __name__ == "__main__":

@@ -9,8 +9,8 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
-    "H0M5": ["CS_HOIST_E=0", "CS_MINB=5"],
-    "H0M4": ["CS_HOIST_E=0"],
+    "N2M3": ["CS_NP2=1", "CS_MINB=3"],
+    "N1M3": ["CS_MINB=3"],
 }
 
 if __name__ == "__main__":

@@ -9,8 +9,9 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
-    "N2M3": ["CS_NP2=1", "CS_MINB=3"],
-    "N1M3": ["CS_MINB=3"],
+    "I8": ["GAP_INS_ITEMS=8"],
+    "I4M4": ["GAP_INS_MINB=4"],
+    "I2M6": ["GAP_INS_ITEMS=2", "GAP_INS_MINB=6"],
 }
 
 if __name__ == "__main__":

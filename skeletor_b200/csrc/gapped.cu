@@ -509,10 +509,11 @@ extern "C" int skb_gap_densify(skb_particles_t in, skb_particles_t out, const in
 
 // the same with the row count read on the device (no host round trip between the kernel
 // that produced the rows and their insertion): a fixed grid strides over the rows
-#ifndef GAP_INS_MINB
-#define GAP_INS_MINB 1
-#endif
+#ifdef GAP_INS_MINB                  // (tuning knob of tools/build_variants.py)
 __global__ void __launch_bounds__(256, GAP_INS_MINB)
+#else
+__global__ void __launch_bounds__(256)
+#endif
 gap_insert_counted_kernel(const double *__restrict__ rows, const int *__restrict__ n_dev,
                           int nmax, skb_particles_t P, const int *__restrict__ gap_start,
                           int *gap_count, KeyParams kp, double *leftover, int leftover_cap,
